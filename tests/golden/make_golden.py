@@ -1,0 +1,168 @@
+"""Mint golden fixtures by running the UNMODIFIED reference on CPU (build container only).
+
+    python tests/golden/make_golden.py
+
+Imports hkchengrex/Tracking-Anything-with-DEVA read-only from /root/reference with the three
+shims of SURVEY.md section 8(c): a stub ``pulp`` module, ``pretrained=False`` ResNets, nothing
+else.  Writes small fixtures next to this file; they pin ``oracle/`` (tests/test_oracle_golden.py)
+and, through it, the CUDA path.  /root/reference does not exist on the GPU box, so nothing at
+test/bench time runs this script.
+"""
+import json
+import os
+import sys
+import types
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.modules['pulp'] = types.ModuleType('pulp')
+sys.path.insert(0, '/root/reference')
+
+import numpy as np
+import torch
+
+import deva.model.resnet as _R  # the reference's deva package
+
+_r18, _r50 = _R.resnet18, _R.resnet50
+_R.resnet18 = lambda pretrained=True, extra_dim=0: _r18(pretrained=False, extra_dim=extra_dim)
+_R.resnet50 = lambda pretrained=True, extra_dim=0: _r50(pretrained=False, extra_dim=extra_dim)
+from deva.inference.inference_core import DEVAInferenceCore
+from deva.inference.memory_manager import MemoryManager
+from deva.model.memory_utils import do_softmax, get_similarity
+from deva.model.network import DEVA
+
+# the product's checkpoint synthesiser (pure python, no CUDA needed) - loaded by path because
+# the package directory shadows the reference's ``deva`` name
+import importlib.util
+
+_spec = importlib.util.spec_from_file_location(
+    'b200_param_spec', os.path.join(ROOT, 'tracking-anything-with-deva_b200', 'deva', 'model', 'param_spec.py'))
+param_spec = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(param_spec)
+
+CFG = dict(key_dim=64, value_dim=512, pix_feat_dim=512, mem_every=5, enable_long_term=True,
+           chunk_size=-1, top_k=30, enable_long_term_count_usage=True, max_mid_term_frames=10,
+           min_mid_term_frames=5, num_prototypes=128, max_long_term_elements=10000)
+torch.set_grad_enabled(False)
+
+
+def save(name, **arrays):
+    np.savez_compressed(os.path.join(HERE, name), **{k: (v.numpy() if torch.is_tensor(v) else v)
+                                                      for k, v in arrays.items()})
+    print('wrote', name, {k: tuple(v.shape) for k, v in arrays.items() if hasattr(v, 'shape')})
+
+
+def golden_spec():
+    sd = DEVA(CFG).state_dict()
+    json.dump({k: list(v.shape) for k, v in sd.items()}, open(os.path.join(HERE, 'checkpoint_spec.json'), 'w'),
+              indent=0)
+    print('wrote checkpoint_spec.json', len(sd))
+
+
+def golden_memory_read():
+    """get_similarity -> do_softmax(top_k, usage) -> _readout on seeded inputs."""
+    torch.manual_seed(0)
+    CK, N, Q, K, CV = 64, 600, 80, 2, 32
+    mk, ms = torch.randn(CK, N), 1 + torch.rand(1, N)
+    qk, qe = torch.randn(CK, Q), torch.sigmoid(torch.randn(CK, Q))
+    mv = torch.randn(K, CV, N)
+    sim = get_similarity(mk, ms, qk, qe, add_batch_dim=True)
+    vals, idx = torch.topk(sim, k=30, dim=1)
+    aff, usage = do_softmax(sim.clone(), top_k=30, inplace=True, return_usage=True)
+    mm = MemoryManager(CFG)
+    out = mm._readout(aff[0], mv)
+    # full-softmax branch used by consolidation (memory_utils.py:66-71)
+    aff_full = do_softmax(sim.clone())
+    save('memory_read.npz', mk=mk, ms=ms, qk=qk, qe=qe, mv=mv, sim=sim[0], topk_idx=idx[0], topk_val=vals[0],
+         affinity=aff[0], usage=usage[0], readout=out, affinity_full=aff_full[0])
+
+
+def golden_bank_trace():
+    """Weight-independent (work,long) size trace, SURVEY.md section 8(c)."""
+    torch.manual_seed(0)
+    cfg = dict(CFG, mem_every=1, max_long_term_elements=400)
+    net = DEVA(cfg).eval()
+    core = DEVAInferenceCore(net, cfg)
+    H = W = 96
+    trace = []
+    for t in range(40):
+        img = torch.randn(3, H, W)
+        if t == 0:
+            m = torch.zeros(H, W, dtype=torch.long); m[8:40, 8:40] = 1; m[50:90, 50:90] = 2
+            core.step(img, m, [1, 2])
+        elif t == 12:
+            m = torch.zeros(H, W, dtype=torch.long); m[8:30, 60:90] = 7
+            core.step(img, m, [7])
+        else:
+            core.step(img)
+        mem = core.memory
+        trace.append({str(b): [mem.work_mem.size(b), mem.long_mem.size(b)] for b in mem.work_mem.buckets})
+    json.dump({'config': cfg, 'hw': 36, 'trace': trace, 'tmp_ids': {str(o.id): t for o, t in
+                                                                     core.object_manager.obj_to_tmp_id.items()}},
+              open(os.path.join(HERE, 'bank_trace.json'), 'w'))
+    print('wrote bank_trace.json', trace[9], trace[24], trace[36])
+
+
+def golden_network():
+    """Stage outputs of the reference network with the synthetic checkpoint (seed 1)."""
+    sd = param_spec.synthetic_state_dict(seed=1)
+    net = DEVA(CFG).eval()
+    net.load_weights(sd)
+    g = torch.Generator().manual_seed(5)
+    H, W, K = 64, 80, 2
+    image = torch.randn(1, 3, H, W, generator=g)
+    masks = torch.zeros(1, K, H, W); masks[0, 0, 5:30, 5:40] = 1; masks[0, 1, 30:60, 30:75] = 1
+    ms, feat = net.encode_image(image)
+    key, shr, sel = net.transform_key(feat)
+    h, w = key.shape[-2:]
+    sensory0 = 0.5 * torch.randn(1, K, 512, h, w, generator=g)
+    value, sensory1 = net.encode_mask(image, ms, sensory0, masks, is_deep_update=True)
+    readout = torch.randn(1, K, 512, h, w, generator=g)
+    sensory2, logits, prob = net.segment(ms, readout, sensory1, masks, update_sensory=True)
+    agg = net.aggregate(masks[0] * 0.9, dim=0)
+    save('network_stages.npz', image=image, masks=masks, f16=ms[0], f8=ms[1], f4=ms[2], feat=feat, key=key,
+         shrinkage=shr, selection=sel, sensory0=sensory0, value=value, sensory1=sensory1, readout=readout,
+         sensory2=sensory2, logits=logits, prob=prob, aggregate=agg)
+    for n, t in dict(f16=ms[0], f8=ms[1], f4=ms[2], key=key, shr=shr, value=value, sensory2=sensory2,
+                     logits=logits).items():
+        print(f'  {n}: mean {t.mean():.3f} std {t.std():.3f} absmax {t.abs().max():.3f}')
+
+
+def golden_vos():
+    """DEVAInferenceCore.step over a 16-frame synthetic clip (objects {1,2}, new object 7 at t=6)."""
+    sd = param_spec.synthetic_state_dict(seed=1)
+    cfg = dict(CFG, mem_every=1, max_long_term_elements=300)
+    net = DEVA(cfg).eval()
+    net.load_weights(sd)
+    np.random.seed(42)
+    core = DEVAInferenceCore(net, cfg)
+    g = torch.Generator().manual_seed(11)
+    H, W, T = 80, 96, 16
+    base = torch.randn(3, H, W, generator=g)
+    frames = torch.stack([base + 0.2 * torch.randn(3, H, W, generator=g) for _ in range(T)])
+    m0 = torch.zeros(H, W, dtype=torch.long); m0[6:40, 6:44] = 1; m0[44:76, 40:90] = 2
+    m6 = torch.zeros(H, W, dtype=torch.long); m6[10:34, 56:92] = 7
+    probs, sizes = [], []
+    for t in range(T):
+        if t == 0:
+            p = core.step(frames[t], m0, [1, 2])
+        elif t == 6:
+            p = core.step(frames[t], m6, [7])
+        else:
+            p = core.step(frames[t], end=(t == T - 1))
+        probs.append(p.clone())
+        mem = core.memory
+        sizes.append({str(b): [mem.work_mem.size(b), mem.long_mem.size(b)] for b in mem.work_mem.buckets})
+    arrays = {f'prob_{t:02d}': p for t, p in enumerate(probs)}
+    save('vos_steps.npz', frames=frames, mask0=m0, mask6=m6, **arrays)
+    json.dump({'config': cfg, 'sizes': sizes}, open(os.path.join(HERE, 'vos_steps.json'), 'w'))
+    print('  sizes', sizes[-1], 'prob range', float(probs[-1].min()), float(probs[-1].max()))
+
+
+if __name__ == '__main__':
+    golden_spec()
+    golden_memory_read()
+    golden_bank_trace()
+    golden_network()
+    golden_vos()
