@@ -1,0 +1,112 @@
+/*
+ * deva_b200 - C ABI of the B200-native temporal-propagation kernels behind DEVA's
+ * DEVAInferenceCore.step / MemoryManager API.
+ *
+ * The reference (hkchengrex/Tracking-Anything-with-DEVA @ 404a112) is pure Python/PyTorch and has no
+ * FFI of its own; the boundary it exposes for this path is the set of Python call sites cited on each
+ * entry point below.  A maintainer binds this library with ctypes; the shipped
+ * drop-in package does exactly that (tracking-anything-with-deva_b200/deva/_native.py).
+ *
+ * Conventions
+ *  - every pointer is a CUDA device pointer unless marked HOST; fp16 buffers are passed as void*;
+ *  - `stream` is a cudaStream_t (0 = legacy default stream); calls only enqueue work and never
+ *    synchronise; inputs are borrowed until the enqueued work completes, outputs are caller-allocated;
+ *  - return 0 on success; otherwise a non-zero code, with text available from deva_b200_last_error()
+ *    (thread-local).  The Python side raises RuntimeError, mirroring the reference's exceptions;
+ *  - "window" = the contiguous run of valid memory slots of one bucket's bank; slot indices in the
+ *    outputs are relative to the window start.  The first `n_lead` (< 8) slots of a window are
+ *    alignment padding and are masked out.
+ */
+#ifndef DEVA_B200_H_
+#define DEVA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEVA_B200_ABI_VERSION 1
+#define DEVA_B200_LIST_PITCH 32 /* row pitch of top-k outputs == max supported top_k */
+#define DEVA_B200_MAX_GROUPS 256 /* objects per deva_b200_readout call */
+
+typedef void* deva_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define DEVA_B200_API __attribute__((visibility("default")))
+#else
+#define DEVA_B200_API
+#endif
+
+DEVA_B200_API int deva_b200_abi_version(void);
+DEVA_B200_API const char* deva_b200_last_error(void);
+/* 0 when the current CUDA device can run the sm_100a kernels. */
+DEVA_B200_API int deva_b200_device_check(void);
+
+/* ---- query side ------------------------------------------------------------------------------------
+ * Packs the per-frame query operand of get_similarity (deva/model/memory_utils.py:24-32):
+ * row q = [ -qe[:,q] | 2*qk[:,q]*qe[:,q] ] split into fp16 (hi, lo), and bsq[q] = sum_c qe*qk^2.
+ * Element (c, q) of qk/qe is read at c*stride_c + q*stride_q (channel-major [CK,Q]: stride_c=Q, stride_q=1).
+ * q_hi/q_lo: [q, 2*ck] fp16;  bsq: [q] fp32.  ck in {32, 64}. */
+DEVA_B200_API int deva_b200_pack_query(const float* qk, const float* qe, int64_t stride_c, int64_t stride_q, int ck, int q,
+                         void* q_hi, void* q_lo, float* bsq, deva_stream_t stream);
+
+/* ---- bank append -----------------------------------------------------------------------------------
+ * Replaces the torch.cat growth of KeyValueMemoryStore.add (deva/inference/kv_memory_store.py:97-116):
+ * writes `n` new tokens at the destination pointers (already offset to the first new slot).
+ * key/selection element (c, t) at c*stride_c + t*stride_t; shrinkage [n].  selection/raw_sel may be NULL.
+ * k_hi/k_lo: [n, 2*ck] fp16 rows [ s*k^2 | s*k ], s = shrinkage/sqrt(ck);  neg_s: [n] = -s;
+ * raw_key/raw_sel: [n, ck] fp32 token-major copies;  raw_shr: [n]. */
+DEVA_B200_API int deva_b200_pack_keys(const float* key, const float* selection, int64_t stride_c, int64_t stride_t,
+                        const float* shrinkage, int ck, int n, void* k_hi, void* k_lo, float* neg_s, float* raw_key,
+                        float* raw_sel, float* raw_shr, deva_stream_t stream);
+/* Value rows fp32 src[r, j] (ld_src) -> fp16 dst[r, j] (ld_dst), r < rows, j < n
+ * (MemoryManager.add_memory, deva/inference/memory_manager.py:199-205). */
+DEVA_B200_API int deva_b200_append_values(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int rows, int n,
+                            deva_stream_t stream);
+
+/* ---- memory read -----------------------------------------------------------------------------------
+ * get_similarity + do_softmax(top_k, inplace, return_usage) (deva/model/memory_utils.py:6-76) and the
+ * usage bookkeeping of MemoryManager.match_memory / update_bucket_usage
+ * (deva/inference/memory_manager.py:115-150, kv_memory_store.py:118-125), fused.
+ *   workspace: deva_b200_simtopk_workspace_bytes(q) bytes of scratch;
+ *   out_idx/out_w: [q, 32] int32 / fp32, entries sorted by descending similarity, zero beyond top_k;
+ *   affinity (optional): [q, ld_affinity] fp16 dense rows (zero-filled, top_k non-zeros per row) for
+ *                        deva_b200_readout;
+ *   use_cnt/life_cnt (optional): [n_window] fp32 counters; slots < n_long are long-term memory;
+ *   count_long/count_work: which region(s) receive usage (+= affinity row sums) and life (+= 1). */
+DEVA_B200_API size_t deva_b200_simtopk_workspace_bytes(int q);
+DEVA_B200_API int deva_b200_sim_topk(const void* k_hi, const void* k_lo, const float* neg_s, int n_window, int n_lead,
+                       const void* q_hi, const void* q_lo, const float* bsq, int q, int ck, int top_k,
+                       void* workspace, int32_t* out_idx, float* out_w, void* affinity, int64_t ld_affinity,
+                       float* use_cnt, float* life_cnt, int n_long, int count_long, int count_work,
+                       deva_stream_t stream);
+/* get_similarity + do_softmax without top-k (max-subtracted branch, memory_utils.py:66-71) as used by
+ * MemoryManager.consolidation (memory_manager.py:262-273).  sim_ws: [q, ld_sim] fp32 scratch;
+ * affinity: [q, ld_affinity] fp16;  shr_out[q] = sum_n affinity[q,n]*shrinkage[n] (optional). */
+DEVA_B200_API int deva_b200_sim_dense_softmax(const void* k_hi, const void* k_lo, const float* neg_s, const float* shrinkage,
+                                int n_window, int n_lead, const void* q_hi, const void* q_lo, const float* bsq,
+                                int q, int ck, float* sim_ws, int64_t ld_sim, void* affinity, int64_t ld_affinity,
+                                float* shr_out, deva_stream_t stream);
+/* MemoryManager._readout (deva/inference/memory_manager.py:64-75):
+ * out[out_row[g] + r, j] = sum_n values[val_row[g] + r, n] * affinity[j, n]
+ * for g < n_groups, r < rows_per_group (multiple of 128), j < q, n < n_window.
+ * values: fp16 [values_rows, values_ld] already offset to the window start; val_row/out_row: HOST int32 arrays. */
+DEVA_B200_API int deva_b200_readout(const void* values, int64_t values_ld, int64_t values_rows, const int32_t* val_row,
+                      const int32_t* out_row, int n_groups, int rows_per_group, const void* affinity,
+                      int64_t ld_affinity, int n_window, int q, float* out, int64_t ld_out, deva_stream_t stream);
+
+/* ---- bank compaction (sieve_by_range / remove_obsolete_features, kv_memory_store.py:127-185) ----------
+ * dst must not alias src.  idx: device int32 [n]. */
+DEVA_B200_API int deva_b200_gather_rows(void* dst, const void* src, const int32_t* idx, int n, int row_bytes, deva_stream_t stream);
+DEVA_B200_API int deva_b200_gather_f32(float* dst, const float* src, const int32_t* idx, int n, deva_stream_t stream);
+DEVA_B200_API int deva_b200_gather_cols_f16(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const int32_t* idx,
+                              int rows, int n, deva_stream_t stream);
+/* usage[i] = use_cnt[i] / life_cnt[i]  (KeyValueMemoryStore.get_usage, kv_memory_store.py:187-193) */
+DEVA_B200_API int deva_b200_usage(float* out, const float* use_cnt, const float* life_cnt, int n, deva_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEVA_B200_H_ */

@@ -1,0 +1,179 @@
+"""GPU parity: C-ABI memory-read kernels vs the CPU oracle (oracle/memory_math.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import memory_math as mm
+
+pytestmark = pytest.mark.gpu
+CK = 64
+
+
+def _native():
+    from deva import _native
+    _native.require_device()
+    return _native
+
+
+def _make(n, q, k_obj, cv, seed, lead=0):
+    g = torch.Generator().manual_seed(seed)
+    mk = torch.randn(CK, n, generator=g)
+    ms = 1 + torch.rand(n, generator=g)
+    qk = torch.randn(CK, q, generator=g)
+    qe = torch.sigmoid(torch.randn(CK, q, generator=g))
+    mv = torch.randn(k_obj * cv, n, generator=g)
+    return mk, ms, qk, qe, mv
+
+
+class Bank:
+    """Minimal packed bank for the kernel tests (the product's bank lives in deva.inference)."""
+    def __init__(self, nat, mk, ms, mv, lead=0):
+        dev = 'cuda'
+        n = mk.shape[1]
+        self.n, self.lead = n, lead
+        nw = n + lead
+        self.nw = nw
+        self.k_hi = torch.zeros(nw, 2 * CK, dtype=torch.float16, device=dev)
+        self.k_lo = torch.zeros_like(self.k_hi)
+        self.neg_s = torch.zeros(nw, device=dev)
+        self.raw_key = torch.zeros(nw, CK, device=dev)
+        self.raw_shr = torch.zeros(nw, device=dev)
+        mk_d, ms_d = mk.to(dev).contiguous(), ms.to(dev).contiguous()
+        nat.pack_keys(mk_d, None, n, 1, ms_d, CK, n, self.k_hi[lead:], self.k_lo[lead:], self.neg_s[lead:],
+                      self.raw_key[lead:], None, self.raw_shr[lead:])
+        rows = mv.shape[0]
+        self.ld = (nw + 7) // 8 * 8 + 64
+        self.values = torch.zeros(rows, self.ld, dtype=torch.float16, device=dev)
+        nat.append_values(mv.to(dev).contiguous(), n, self.values[:, lead:], self.ld, rows, n)
+        self.use = torch.zeros(nw, device=dev)
+        self.life = torch.zeros(nw, device=dev) + 1e-7
+
+
+def _read(nat, bank, qk, qe, k_obj, cv, top_k=30):
+    dev = 'cuda'
+    q = qk.shape[1]
+    q_hi = torch.empty(q, 2 * CK, dtype=torch.float16, device=dev)
+    q_lo = torch.empty_like(q_hi)
+    bsq = torch.empty(q, device=dev)
+    qk_d, qe_d = qk.to(dev).contiguous(), qe.to(dev).contiguous()
+    nat.pack_query(qk_d, qe_d, q, 1, CK, q, q_hi, q_lo, bsq)
+    ws = torch.empty(nat.simtopk_workspace_bytes(q), dtype=torch.uint8, device=dev)
+    idx = torch.empty(q, 32, dtype=torch.int32, device=dev)
+    w = torch.empty(q, 32, device=dev)
+    ldp = (bank.nw + 7) // 8 * 8
+    P = torch.empty(q, ldp, dtype=torch.float16, device=dev)
+    nat.sim_topk(bank.k_hi, bank.k_lo, bank.neg_s, bank.nw, bank.lead, q_hi, q_lo, bsq, q, CK, top_k, ws, idx, w, P,
+                 ldp, bank.use, bank.life, bank.lead, False, True)
+    out = torch.empty(k_obj * cv, q, device=dev)
+    nat.readout(bank.values, bank.ld, k_obj * cv, [i * cv for i in range(k_obj)], [i * cv for i in range(k_obj)], cv,
+                P, ldp, bank.nw, q, out, q)
+    torch.cuda.synchronize()
+    return idx.cpu(), w.cpu(), P.float().cpu(), out.cpu(), (q_hi, q_lo, bsq)
+
+
+def _check_read(n, q, k_obj, cv, seed, lead=0, top_k=30):
+    nat = _native()
+    mk, ms, qk, qe, mv = _make(n, q, k_obj, cv, seed)
+    bank = Bank(nat, mk, ms, mv, lead)
+    idx, w, P, out, _ = _read(nat, bank, qk, qe, k_obj, cv, top_k)
+    sim = mm.similarity(mk.double(), ms.double(), qk.double(), qe.double())
+    ref_idx, ref_w = mm.topk_softmax(sim, top_k)  # [k, Q]
+    idx = idx[:, :top_k].long() - lead
+    assert int(idx.min()) >= 0 and int(idx.max()) < n
+    # membership: identical sets except where the k-th / (k+1)-th similarities are within 2e-4
+    srt = torch.sort(sim, 0, descending=True)[0]
+    gap = (srt[top_k - 1] - srt[top_k]).abs() if n > top_k else torch.full((q, ), 1.0, dtype=sim.dtype)
+    same = torch.tensor([set(idx[i].tolist()) == set(ref_idx[:, i].tolist()) for i in range(q)])
+    assert bool((same | (gap < 2e-4)).all()), f'top-k sets differ on {int((~same).sum())} queries'
+    # values at the selected slots match fp64 similarity to ~fp32 accuracy
+    sel_sim = torch.gather(sim.t(), 1, idx)  # [Q, k]
+    e = torch.exp(sel_sim - sel_sim.max(1, keepdim=True)[0])
+    w_ref = (e / e.sum(1, keepdim=True)).float()
+    assert float((w[:, :top_k] - w_ref).abs().max()) < 2e-5
+    assert bool((w[:, top_k:] == 0).all())
+    # sorted by descending similarity
+    assert bool((sel_sim[:, :-1] - sel_sim[:, 1:] > -2e-4).all())
+    # dense affinity rows and usage
+    aff = torch.zeros(q, bank.nw).scatter_(1, idx + lead, w[:, :top_k])
+    assert float((P[:, :bank.nw] - aff).abs().max()) < 6e-4  # fp16 rounding of weights in [0,1]
+    usage = bank.use.cpu()
+    assert float((usage - aff.sum(0)).abs().max()) < 1e-4
+    assert float((bank.life.cpu()[lead:] - 1.0).abs().max()) < 1e-5
+    # readout: fp16 operands, fp32 accumulate
+    ref_out = mm.readout(mm.dense_affinity(sim, top_k), mv.double()).float()
+    err = float((out - ref_out).abs().max())
+    scale = float(ref_out.abs().max())
+    assert err < 4e-3 * max(1.0, scale), (err, scale)
+    if bool(same.all()):
+        # against the same fp16-rounded operands the GEMM must be fp32-exact
+        ref16 = (mv.half().double() @ P[:, lead:lead + n].double().t()).float()
+        assert float((out - ref16).abs().max()) < 2e-4 * max(1.0, scale)
+    return err
+
+
+def test_operand_split_is_fp32_accurate():
+    nat = _native()
+    mk, ms, qk, qe, mv = _make(300, 50, 1, 128, 3)
+    bank = Bank(nat, mk, ms, mv)
+    s = ms / 8.0
+    want = torch.cat([(s * mk * mk).t(), (s * mk).t()], 1)
+    got = bank.k_hi.float().cpu().double() + bank.k_lo.float().cpu().double()
+    assert float((got - want.double()).abs().max()) < 2e-6 * float(want.abs().max())
+    assert torch.equal(bank.raw_key.cpu(), mk.t().contiguous())
+    assert float((bank.neg_s.cpu() + s).abs().max()) < 1e-6
+
+
+def test_golden_fixture(golden_dir):
+    """The reference-minted fixture, through the CUDA path."""
+    nat = _native()
+    g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, 'memory_read.npz')).items()}
+    mk, ms, qk, qe = g['mk'], g['ms'].reshape(-1), g['qk'], g['qe']
+    mv = torch.zeros(256, mk.shape[1])
+    mv[:64] = g['mv'].flatten(0, 1)
+    bank = Bank(nat, mk, ms, mv)
+    idx, w, P, out, _ = _read(nat, bank, qk, qe, 2, 128)
+    ref_idx = g['topk_idx'].t()
+    assert all(set(idx[i, :30].tolist()) == set(ref_idx[i].tolist()) for i in range(idx.shape[0]))
+    assert float((bank.use.cpu() - g['usage']).abs().max()) < 1e-4
+    got = torch.cat([out[:32], out[128:160]]).view(2, 32, -1)
+    assert float((got - g['readout']).abs().max()) < 4e-3
+
+
+@pytest.mark.parametrize('n,q,k_obj,cv,lead', [
+    (30, 5, 1, 128, 0),          # N == top_k, one partial tile
+    (257, 37, 1, 128, 3),        # ragged everything, masked lead slots
+    (1000, 300, 2, 256, 5),
+    (2000, 1620, 5, 512, 0),     # BASELINE config 2
+])
+def test_read_matches_oracle(n, q, k_obj, cv, lead):
+    _check_read(n, q, k_obj, cv, seed=n + q, lead=lead)
+
+
+def test_small_topk():
+    _check_read(500, 64, 1, 128, seed=9, top_k=7)
+
+
+def test_dense_softmax_matches_oracle():
+    nat = _native()
+    n, q = 900, 128
+    mk, ms, qk, qe, mv = _make(n, q, 1, 128, 21)
+    bank = Bank(nat, mk, ms, mv, lead=2)
+    dev = 'cuda'
+    q_hi = torch.empty(q, 2 * CK, dtype=torch.float16, device=dev)
+    q_lo = torch.empty_like(q_hi)
+    bsq = torch.empty(q, device=dev)
+    nat.pack_query(qk.to(dev).contiguous(), qe.to(dev).contiguous(), q, 1, CK, q, q_hi, q_lo, bsq)
+    ld = (bank.nw + 7) // 8 * 8
+    sim_ws = torch.empty(q, ld, device=dev)
+    P = torch.zeros(q, ld, dtype=torch.float16, device=dev)
+    shr_out = torch.empty(q, device=dev)
+    nat.sim_dense_softmax(bank.k_hi, bank.k_lo, bank.neg_s, bank.raw_shr, bank.nw, bank.lead, q_hi, q_lo, bsq, q, CK,
+                          sim_ws, ld, P, ld, shr_out)
+    torch.cuda.synchronize()
+    sim = mm.similarity(mk, ms, qk, qe)
+    assert float((sim_ws.cpu()[:, 2:2 + n] - sim.t()).abs().max()) < 1e-4
+    aff = mm.dense_affinity(sim, None)
+    assert float((P.float().cpu()[:, 2:2 + n] - aff.t()).abs().max()) < 6e-4
+    assert float((shr_out.cpu() - (ms.reshape(1, -1) @ aff).reshape(-1)).abs().max()) < 1e-4

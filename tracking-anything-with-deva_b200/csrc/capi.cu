@@ -1,0 +1,82 @@
+// extern "C" surface of libdeva_b200.so; declarations and reference citations live in include/deva_b200.h.
+#include "../../include/deva_b200.h"
+
+#include <cuda_fp16.h>
+
+#include "bank_ops.h"
+#include "common.h"
+#include "readout.h"
+#include "simtopk.h"
+
+namespace b200 { const char* last_error(); }
+using namespace b200;
+
+static inline cudaStream_t S(deva_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline __half* H(void* p) { return reinterpret_cast<__half*>(p); }
+static inline const __half* H(const void* p) { return reinterpret_cast<const __half*>(p); }
+
+extern "C" {
+
+DEVA_B200_API int deva_b200_abi_version(void) { return DEVA_B200_ABI_VERSION; }
+DEVA_B200_API const char* deva_b200_last_error(void) { return last_error(); }
+
+DEVA_B200_API int deva_b200_device_check(void) {
+  int dev = 0, major = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  B200_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  B200_REQUIRE(major == 10, "deva_b200 kernels are built for sm_100a; device has compute capability major %d", major);
+  return 0;
+}
+
+DEVA_B200_API int deva_b200_pack_query(const float* qk, const float* qe, int64_t stride_c, int64_t stride_q, int ck, int q,
+                         void* q_hi, void* q_lo, float* bsq, deva_stream_t stream) {
+  return launch_pack_query(qk, qe, stride_c, stride_q, ck, q, H(q_hi), H(q_lo), bsq, S(stream));
+}
+DEVA_B200_API int deva_b200_pack_keys(const float* key, const float* selection, int64_t stride_c, int64_t stride_t,
+                        const float* shrinkage, int ck, int n, void* k_hi, void* k_lo, float* neg_s, float* raw_key,
+                        float* raw_sel, float* raw_shr, deva_stream_t stream) {
+  return launch_pack_keys(key, selection, stride_c, stride_t, shrinkage, ck, n, H(k_hi), H(k_lo), neg_s, raw_key,
+                          raw_sel, raw_shr, S(stream));
+}
+DEVA_B200_API int deva_b200_append_values(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int rows, int n,
+                            deva_stream_t stream) {
+  return launch_append_values(src, ld_src, H(dst), ld_dst, rows, n, S(stream));
+}
+DEVA_B200_API size_t deva_b200_simtopk_workspace_bytes(int q) { return simtopk_workspace_bytes(q); }
+DEVA_B200_API int deva_b200_sim_topk(const void* k_hi, const void* k_lo, const float* neg_s, int n_window, int n_lead,
+                       const void* q_hi, const void* q_lo, const float* bsq, int q, int ck, int top_k,
+                       void* workspace, int32_t* out_idx, float* out_w, void* affinity, int64_t ld_affinity,
+                       float* use_cnt, float* life_cnt, int n_long, int count_long, int count_work,
+                       deva_stream_t stream) {
+  return launch_sim_topk(H(k_hi), H(k_lo), neg_s, n_window, n_lead, H(q_hi), H(q_lo), bsq, q, ck, top_k, workspace,
+                         out_idx, out_w, H(affinity), ld_affinity, use_cnt, life_cnt, n_long, count_long, count_work,
+                         S(stream));
+}
+DEVA_B200_API int deva_b200_sim_dense_softmax(const void* k_hi, const void* k_lo, const float* neg_s, const float* shrinkage,
+                                int n_window, int n_lead, const void* q_hi, const void* q_lo, const float* bsq,
+                                int q, int ck, float* sim_ws, int64_t ld_sim, void* affinity, int64_t ld_affinity,
+                                float* shr_out, deva_stream_t stream) {
+  return launch_sim_dense_softmax(H(k_hi), H(k_lo), neg_s, shrinkage, n_window, n_lead, H(q_hi), H(q_lo), bsq, q, ck,
+                                  sim_ws, ld_sim, H(affinity), ld_affinity, shr_out, S(stream));
+}
+DEVA_B200_API int deva_b200_readout(const void* values, int64_t values_ld, int64_t values_rows, const int32_t* val_row,
+                      const int32_t* out_row, int n_groups, int rows_per_group, const void* affinity,
+                      int64_t ld_affinity, int n_window, int q, float* out, int64_t ld_out, deva_stream_t stream) {
+  return launch_readout(H(values), values_ld, values_rows, val_row, out_row, n_groups, rows_per_group, H(affinity),
+                        ld_affinity, n_window, q, out, ld_out, S(stream));
+}
+DEVA_B200_API int deva_b200_gather_rows(void* dst, const void* src, const int32_t* idx, int n, int row_bytes, deva_stream_t stream) {
+  return launch_gather_rows(dst, src, idx, n, row_bytes, S(stream));
+}
+DEVA_B200_API int deva_b200_gather_f32(float* dst, const float* src, const int32_t* idx, int n, deva_stream_t stream) {
+  return launch_gather_f32(dst, src, idx, n, S(stream));
+}
+DEVA_B200_API int deva_b200_gather_cols_f16(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, const int32_t* idx,
+                              int rows, int n, deva_stream_t stream) {
+  return launch_gather_cols_f16(H(dst), ld_dst, H(src), ld_src, idx, rows, n, S(stream));
+}
+DEVA_B200_API int deva_b200_usage(float* out, const float* use_cnt, const float* life_cnt, int n, deva_stream_t stream) {
+  return launch_usage(out, use_cnt, life_cnt, n, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,13 @@
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace b200 {
+constexpr int kMaxGroups = 256;  // objects per readout launch
+
+// out[out_row[g] + r, q] = sum_n values[val_row[g] + r, n] * P[q, n]
+// for g < n_groups, r < rows_per_group, q < q, n < n_window.  val_row/out_row are HOST arrays.
+int launch_readout(const __half* values, long long values_ld, long long values_rows, const int* val_row,
+                   const int* out_row, int n_groups, int rows_per_group, const __half* P, long long ldP,
+                   int n_window, int q, float* out, long long ldo, cudaStream_t stream);
+}  // namespace b200

@@ -1,0 +1,16 @@
+"""Drop-in ``deva`` package: DEVA's propagation API on B200-native kernels.
+
+Same import surface as the reference (deva/__init__.py:1-2): ``deva.DEVAInferenceCore`` and
+``deva.DEVA``.  Imports are lazy so that pure-host modules (checkpoint spec, object bookkeeping)
+stay importable on machines without a GPU.
+"""
+
+
+def __getattr__(name):
+    if name == 'DEVAInferenceCore':
+        from deva.inference.inference_core import DEVAInferenceCore
+        return DEVAInferenceCore
+    if name == 'DEVA':
+        from deva.model.network import DEVA
+        return DEVA
+    raise AttributeError(name)
