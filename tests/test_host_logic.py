@@ -1,0 +1,156 @@
+"""CPU tests: host-side id/padding/merging logic and the C-ABI export surface (no GPU compute)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.core import ObjectTable, crop_pad, pad_to_multiple
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_pad_unpad_match_oracle():
+    from deva.utils.tensor_utils import pad_divide_by, unpad
+    for h, w in [(480, 854), (1080, 1920), (96, 96), (17, 33), (5, 7)]:
+        x = torch.arange(3 * h * w, dtype=torch.float32).view(3, h, w)
+        y, pad = pad_divide_by(x, 16)
+        ref, rpad = pad_to_multiple(x, 16)
+        assert tuple(pad) == tuple(rpad) and torch.equal(y, ref)
+        assert y.shape[-1] % 16 == 0 and y.shape[-2] % 16 == 0
+        assert torch.equal(unpad(y, pad), x) and torch.equal(crop_pad(ref, rpad), x)
+        assert torch.equal(unpad(y.unsqueeze(0), pad), x.unsqueeze(0))
+
+
+def test_object_manager_ids_bit_exact():
+    from deva.inference.object_manager import ObjectManager
+    np.random.seed(7)
+    om = ObjectManager()
+    tmp, ids = om.add_new_objects([1, 2, 5])
+    assert tmp == [1, 2, 3] and ids == [1, 2, 5]
+    tmp2, ids2 = om.add_new_objects([2])  # collision -> random re-id drawn from numpy's global RNG
+    np.random.seed(7)
+    ref = ObjectTable()
+    ref.add([1, 2, 5])
+    ref.add([2])
+    assert {t: o.id for t, o in om.tmp_id_to_obj.items()} == ref.tmp_to_id
+    mask = torch.tensor([[0, 1, 2], [3, 4, 4]])
+    assert torch.equal(om.tmp_to_obj_cls(mask), ref.to_object_ids(mask))
+    assert om.all_obj_ids == ref.ids and om.num_obj == 4
+    assert om.has_all([1, 5]) and not om.has_all([1, 99])
+    om.delete_object([2])
+    assert [o.id for o in om.tmp_id_to_obj.values()] == [1, 5, ids2[0]]
+    assert list(om.tmp_id_to_obj.keys()) == [1, 2, 3]
+    one_hot = om.make_one_hot(torch.tensor([[1, 5], [0, ids2[0]]]))
+    assert one_hot.shape == (3, 2, 2) and one_hot.sum().item() == 3
+    d = {o.id: torch.full((2, 2), float(o.id)) for o in om.tmp_id_to_obj.values()}
+    assert om.realize_dict(d)[:, 0, 0].tolist() == [1.0, 5.0, float(ids2[0])]
+    # zero-copy path: consecutive slices of one buffer come back as a view
+    buf = torch.arange(12.).view(3, 2, 2)
+    view = om.realize_dict({o.id: buf[i] for i, o in enumerate(om.tmp_id_to_obj.values())})
+    assert view.data_ptr() == buf.data_ptr() and torch.equal(view, buf)
+
+
+def test_purge_inactive():
+    from deva.inference.object_manager import ObjectManager
+    om = ObjectManager()
+    om.add_new_objects([3, 4, 9])
+    om.find_object_by_id(4).poke_count = 6
+    purged, tmp_keep, obj_keep = om.purge_inactive_objects(5)
+    assert purged and tmp_keep == [1, 3] and obj_keep == [3, 9]
+    assert {t: o.id for t, o in om.tmp_id_to_obj.items()} == {1: 3, 2: 9}
+
+
+def _merge_reference(our_mask, new_mask, our, dets):
+    """Straight restatement of the reference's greedy IoU merge (segment_merging.py:17-143), ids only."""
+    merged = torch.zeros_like(our_mask)
+    next_tmp = len(our)
+    result_ids = dict(our)  # obj id -> tmp
+    area, matched = {}, {}
+    for d in dets:
+        dm = new_mask == d
+        for oid, tmp in our.items():
+            if oid in matched:
+                continue
+            om_ = our_mask == tmp
+            inter = int((dm & om_).sum())
+            if inter == 0:
+                continue
+            union = int(dm.sum()) + int(om_.sum()) - inter
+            if inter / union > 0.5:
+                matched[oid] = d
+                area[(oid, False)] = union
+                break
+        else:
+            area[(d, True)] = int(dm.sum())
+    for oid, tmp in our.items():
+        if oid not in matched:
+            area[(oid, False)] = int((our_mask == tmp).sum())
+    for (x, is_new), _ in sorted(area.items(), key=lambda kv: kv[1], reverse=True):
+        if is_new:
+            next_tmp += 1
+            result_ids[x] = next_tmp
+            merged[new_mask == x] = x
+        else:
+            merged[our_mask == our[x]] = x
+            if x in matched:
+                merged[new_mask == matched[x]] = x
+    return merged, result_ids
+
+
+def test_match_and_merge_matches_reference_logic():
+    from deva.inference.object_info import ObjectInfo
+    from deva.inference.object_manager import ObjectManager
+    from deva.inference.segment_merging import match_and_merge
+    g = torch.Generator().manual_seed(0)
+    for trial in range(5):
+        H = W = 24
+        our_mask = torch.zeros(H, W, dtype=torch.long)
+        our_mask[2:12, 2:12] = 1
+        our_mask[12:22, 4:20] = 2
+        new_mask = torch.zeros(H, W, dtype=torch.long)
+        r = int(torch.randint(0, 4, (1, ), generator=g))
+        new_mask[2 + r:12 + r, 2:12] = 40          # overlaps object tmp 1
+        new_mask[0:6, 14:24] = 41                  # new object
+        new_mask[18:24, 0:3] = 42                  # new object, small
+        om = ObjectManager()
+        om.add_new_objects([10, 11])
+        dets = [ObjectInfo(40), ObjectInfo(41), ObjectInfo(42)]
+        out = match_and_merge(our_mask, new_mask, om, dets)
+        want, ids = _merge_reference(our_mask, new_mask, {10: 1, 11: 2}, [40, 41, 42])
+        got_cls = torch.zeros_like(our_mask)
+        for tmp, obj in om.tmp_id_to_obj.items():
+            got_cls[out[tmp - 1]] = obj.id
+        assert torch.equal(got_cls, want), trial
+        assert {o.id: t for o, t in om.obj_to_tmp_id.items()} == ids
+        assert om.find_object_by_id(11).poke_count == 1
+
+
+def test_c_abi_exports_every_declared_symbol():
+    lib_path = os.path.join(ROOT, 'tracking-anything-with-deva_b200', 'csrc', 'libdeva_b200.so')
+    if not os.path.exists(lib_path):
+        import __graft_entry__
+        __graft_entry__.build()
+    header = open(os.path.join(ROOT, 'include', 'deva_b200.h')).read()
+    declared = set(re.findall(r'DEVA_B200_API[^;(]*?\b(deva_b200_\w+)\s*\(', header))
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    from deva import _native
+    assert set(_native.EXPORTS) == declared
+    assert _native.lib().deva_b200_abi_version() == 1  # loads without a GPU; no compute is launched
+
+
+def test_native_refuses_to_run_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from deva import _native
+    with pytest.raises(RuntimeError):
+        _native.require_device()
+    from deva.model.network import DEVA
+    net = DEVA(dict(key_dim=64, value_dim=512, pix_feat_dim=512))
+    with pytest.raises(RuntimeError):
+        net.encode_image(torch.zeros(1, 3, 32, 32))

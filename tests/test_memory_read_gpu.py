@@ -131,7 +131,8 @@ def test_golden_fixture(golden_dir):
     g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, 'memory_read.npz')).items()}
     mk, ms, qk, qe = g['mk'], g['ms'].reshape(-1), g['qk'], g['qe']
     mv = torch.zeros(256, mk.shape[1])
-    mv[:64] = g['mv'].flatten(0, 1)
+    mv[:32] = g['mv'][0]
+    mv[128:160] = g['mv'][1]
     bank = Bank(nat, mk, ms, mv)
     idx, w, P, out, _ = _read(nat, bank, qk, qe, 2, 128)
     ref_idx = g['topk_idx'].t()

@@ -47,6 +47,54 @@ struct Params {
   long long ld_dense;
 };
 
+
+// Replace the current minimum of this thread's candidate column with (v, n) and find the new minimum.
+// The column has kListCap entries (entries >= top_k hold +inf).  All 32 loads are issued back to back
+// and reduced with a 5-level tree, so one insertion costs ~one shared-memory latency instead of 32.
+struct MinSlot { float thr; int pos; };
+__device__ __noinline__ MinSlot insert_candidate(float* list_val, int* list_idx, int row, float v, int n,
+                                                 int minpos) {
+  list_val[minpos * BQ + row] = v;
+  list_idx[minpos * BQ + row] = n;
+  float x[kListCap];
+  int pos[kListCap / 2];
+#pragma unroll
+  for (int j = 0; j < kListCap; ++j) x[j] = list_val[j * BQ + row];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const bool c = x[j + 16] < x[j];
+    x[j] = c ? x[j + 16] : x[j];
+    pos[j] = c ? j + 16 : j;
+  }
+#pragma unroll
+  for (int w = 8; w >= 1; w >>= 1) {
+#pragma unroll
+    for (int j = 0; j < w; ++j) {
+      const bool c = x[j + w] < x[j];
+      x[j] = c ? x[j + w] : x[j];
+      pos[j] = c ? pos[j + w] : pos[j];
+    }
+  }
+  MinSlot r;
+  r.thr = x[0];
+  r.pos = pos[0];
+  return r;
+}
+
+// v[j] for a run-time j without spilling v to local memory: 5-level select tree (31 selects).
+__device__ __forceinline__ float pick32(const float (&v)[32], int j) {
+  float a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? v[i + 16] : v[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[i + 8] : a[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[i + 4] : b[i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 2) ? c[i + 2] : c[i];
+  return (j & 1) ? d[1] : d[0];
+}
+
 template <bool DENSE>
 __global__ void __launch_bounds__(THREADS, 1)
 simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_ql,
@@ -149,8 +197,8 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     float thr = -CUDART_INF_F;
     int minpos = 0;
     if (!DENSE) {
-      for (int j = 0; j < top_k; ++j) {
-        list_val[j * BQ + row] = -CUDART_INF_F;
+      for (int j = 0; j < kListCap; ++j) {
+        list_val[j * BQ + row] = (j < top_k) ? -CUDART_INF_F : CUDART_INF_F;
         list_idx[j * BQ + row] = -1;
       }
     }
@@ -188,24 +236,21 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
               if (n0 + c * 32 + j < p.n_window) dst[j] = (v[j] == v[j]) ? v[j] : -CUDART_INF_F;
           }
         } else {
-          bool any = false;
+          // Bit j of `pending` = column j beats this query's current k-th best.  Lanes then retire their
+          // pending candidates in lock-step (1st of every lane, 2nd of every lane, ...): the warp pays for
+          // max-per-lane insertions per chunk, not for every distinct column position.
+          uint32_t pending = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) any |= (v[j] > thr);
-          if (any) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (v[j] > thr) {
-                list_val[minpos * BQ + row] = v[j];
-                list_idx[minpos * BQ + row] = n0 + c * 32 + j;
-                float m = CUDART_INF_F;
-                int mp = 0;
-#pragma unroll 1
-                for (int e = 0; e < top_k; ++e) {
-                  const float x = list_val[e * BQ + row];
-                  if (x < m) { m = x; mp = e; }
-                }
-                thr = m;
-                minpos = mp;
+          for (int j = 0; j < 32; ++j) pending |= (v[j] > thr) ? (1u << j) : 0u;
+          while (__any_sync(0xffffffffu, pending != 0)) {
+            if (pending) {
+              const int j = __ffs(pending) - 1;
+              pending &= pending - 1;
+              const float x = pick32(v, j);
+              if (x > thr) {
+                const MinSlot ms = insert_candidate(list_val, list_idx, row, x, n0 + c * 32 + j, minpos);
+                thr = ms.thr;
+                minpos = ms.pos;
               }
             }
           }
@@ -351,6 +396,21 @@ static int make_maps(CUtensorMap* m, const __half* q_hi, const __half* q_lo, int
   return 0;
 }
 
+
+// Split of the memory axis over CTAs: minimise (waves) x (tiles per CTA), with a small per-split
+// charge for the list warm-up every split repeats.
+static int choose_split(int q_tiles, int tiles, int max_split) {
+  const int sms = sm_count();
+  int best = 1;
+  long long best_cost = -1;
+  for (int ns = 1; ns <= max_split && ns <= tiles; ++ns) {
+    const long long waves = ceil_div((long long)q_tiles * ns, sms);
+    const long long cost = waves * (ceil_div(tiles, ns) * 4 + 3);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ns; }
+  }
+  return best;
+}
+
 size_t simtopk_workspace_bytes(int q) {
   const size_t qpad = (size_t)ceil_div(q, 128) * 128;
   return (size_t)kMaxSplit * kListCap * qpad * 8;
@@ -372,9 +432,7 @@ int launch_sim_topk(const __half* k_hi, const __half* k_lo, const float* neg_s, 
   p.q = q; p.n_window = n_window; p.n_lead = n_lead; p.kblocks = 2 * ck / 64; p.top_k = top_k;
   p.tiles_total = ceil_div(n_window, BNK);
   const int q_tiles = ceil_div(q, BQ);
-  int nsplit = ceil_div(sm_count(), q_tiles);
-  if (nsplit > kMaxSplit) nsplit = kMaxSplit;
-  if (nsplit > p.tiles_total) nsplit = p.tiles_total;
+  int nsplit = choose_split(q_tiles, p.tiles_total, kMaxSplit);
   p.tiles_per_split = ceil_div(p.tiles_total, nsplit);
   nsplit = ceil_div(p.tiles_total, p.tiles_per_split);
   p.qpad = q_tiles * BQ;
