@@ -41,6 +41,8 @@ typedef void* deva_stream_t; /* cudaStream_t */
 
 DEVA_B200_API int deva_b200_abi_version(void);
 DEVA_B200_API const char* deva_b200_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py reports it). */
+DEVA_B200_API uint64_t deva_b200_launch_count(void);
 /* 0 when the current CUDA device can run the sm_100a kernels. */
 DEVA_B200_API int deva_b200_device_check(void);
 

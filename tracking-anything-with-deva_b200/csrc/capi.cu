@@ -8,7 +8,7 @@
 #include "readout.h"
 #include "simtopk.h"
 
-namespace b200 { const char* last_error(); }
+namespace b200 { const char* last_error(); unsigned long long launch_count(); }
 using namespace b200;
 
 static inline cudaStream_t S(deva_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -19,6 +19,7 @@ extern "C" {
 
 DEVA_B200_API int deva_b200_abi_version(void) { return DEVA_B200_ABI_VERSION; }
 DEVA_B200_API const char* deva_b200_last_error(void) { return last_error(); }
+DEVA_B200_API uint64_t deva_b200_launch_count(void) { return launch_count(); }
 
 DEVA_B200_API int deva_b200_device_check(void) {
   int dev = 0, major = 0;

@@ -24,7 +24,12 @@ void set_error(const char* fmt, ...);  // stores into the thread-local slot read
     }                                                                                \
   } while (0)
 
-#define B200_LAUNCH_CHECK() B200_CUDA(cudaGetLastError())
+void count_launch();  // bumps the counter read by deva_b200_launch_count()
+#define B200_LAUNCH_CHECK()          \
+  do {                               \
+    ::b200::count_launch();          \
+    B200_CUDA(cudaGetLastError());   \
+  } while (0)
 
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 

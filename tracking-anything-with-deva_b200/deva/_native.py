@@ -6,7 +6,7 @@ error, a RuntimeError is raised.  PyTorch is used for device memory and streams 
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_int, c_int32, c_int64, c_size_t, c_void_p, POINTER
+from ctypes import c_char_p, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p, POINTER
 
 import torch
 
@@ -21,6 +21,7 @@ _lib = None
 _SIGNATURES = {
     'deva_b200_abi_version': (c_int, []),
     'deva_b200_last_error': (c_char_p, []),
+    'deva_b200_launch_count': (c_uint64, []),
     'deva_b200_device_check': (c_int, []),
     'deva_b200_pack_query': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),
@@ -74,6 +75,10 @@ def _ptr(t):
 
 def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(lib().deva_b200_launch_count())
 
 
 def require_device():

@@ -48,6 +48,8 @@ class MemoryManager:
 
         self.config_stale = True
         self.engaged = False
+        # optional profiling hook: a list that receives one (start, end) CUDA-event pair per match_memory call
+        self.read_events = None
 
     def _read_long_term_config(self, config: Dict) -> None:
         self.max_mem_frames = config['max_mid_term_frames']
@@ -100,6 +102,9 @@ class MemoryManager:
         dev = query_key.device
         qk = query_key[0].reshape(self.CK, q).float().contiguous()
         qe = selection[0].reshape(self.CK, q).float().contiguous()
+        if self.read_events is not None:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
         q_hi, q_lo, bsq = self._pack_query(qk, qe, q, 1, q, 'mm_')
 
         order = {obj: i for i, obj in enumerate(self._object_order())}
@@ -124,6 +129,10 @@ class MemoryManager:
                 nat.readout(bank.values[:, :, w0:], bank.cap, bank.values.shape[0] * self.CV,
                             [bank.slot_of[o] * self.CV for o in part], [order[o] * self.CV for o in part], self.CV,
                             aff, ldp, n_window, q, out, q)
+        if self.read_events is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            self.read_events.append((ev0, ev1))
         out = out.view(k_total, self.CV, h, w)
         return {obj: out[i] for obj, i in order.items()}
 
