@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DEVA_B200_ABI_VERSION 1
+#define DEVA_B200_ABI_VERSION 2
 #define DEVA_B200_LIST_PITCH 32 /* row pitch of top-k outputs == max supported top_k */
 #define DEVA_B200_MAX_GROUPS 256 /* objects per deva_b200_readout call */
 
@@ -97,7 +97,10 @@ DEVA_B200_API int deva_b200_sim_dense_softmax(const void* k_hi, const void* k_lo
  * values: fp16 [values_rows, values_ld] already offset to the window start; val_row/out_row: HOST int32 arrays. */
 DEVA_B200_API int deva_b200_readout(const void* values, int64_t values_ld, int64_t values_rows, const int32_t* val_row,
                       const int32_t* out_row, int n_groups, int rows_per_group, const void* affinity,
-                      int64_t ld_affinity, int n_window, int q, float* out, int64_t ld_out, deva_stream_t stream);
+                      int64_t ld_affinity, int n_window, int q, float* out, int64_t ld_out, void* out_tok, deva_stream_t stream);
+/* out_tok (optional; when non-NULL it replaces `out`): fp16 token-major result
+ * out_tok[(object*q + j)*rows_per_group + r] with object = out_row[g] / rows_per_group - the layout the NHWC
+ * decoder kernels consume. */
 
 /* ---- bank compaction (sieve_by_range / remove_obsolete_features, kv_memory_store.py:127-185) ----------
  * dst must not alias src.  idx: device int32 [n]. */
@@ -107,6 +110,64 @@ DEVA_B200_API int deva_b200_gather_cols_f16(void* dst, int64_t ld_dst, const voi
                               int rows, int n, deva_stream_t stream);
 /* usage[i] = use_cnt[i] / life_cnt[i]  (KeyValueMemoryStore.get_usage, kv_memory_store.py:187-193) */
 DEVA_B200_API int deva_b200_usage(float* out, const float* use_cnt, const float* life_cnt, int n, deva_stream_t stream);
+
+/* ==== network path: NHWC fp16 implicit-GEMM convolution + helper kernels ===================================
+ * Activations are fp16 NHWC [batch, h, w, c] with c a multiple of 64 (8 for the helpers); weights are packed
+ * fp16 [cout_pad, kh*kw*cin_pad] (filter tap major, input channel minor), bias fp32 [cout_pad] with the
+ * eval-mode BatchNorm already folded in. */
+typedef struct deva_b200_conv_desc {
+  const void* x;        /* fp16 NHWC input [batch, h, w, cin_pad] */
+  int32_t batch, h, w, cin_pad;
+  const void* w_packed; /* fp16 [cout_pad, kh*kw*cin_pad] */
+  int32_t kh, kw, stride; /* 1x1 or 3x3, stride 1 or 2, padding kh/2 (nn.Conv2d semantics) */
+  int32_t cout, cout_pad, nt; /* real / padded output channels, channel tile (multiple of 32, <= 256, divides cout_pad) */
+  int32_t th, tw;       /* spatial tile of the implicit GEMM, th*tw == 128 */
+  const float* bias;
+  const void* res;      /* optional fp16 NHWC residual added before the activation (shape of the output) */
+  int32_t res_broadcast; /* 1: `res` is ONE image broadcast over the batch */
+  const float* rank1_w; /* optional fp32 [cout_pad]: weight of an extra 1-channel input ... */
+  const float* rank1_x; /* ... whose fp32 plane is [batch, ho*wo]  (out += rank1_w[c] * rank1_x[b, pixel]) */
+  void* out_raw;        /* optional fp16 NHWC output */
+  void* out_relu;       /* optional fp16 NHWC output, ReLU applied */
+  float* out_f32;       /* optional fp32 NHWC output */
+} deva_b200_conv_desc;
+/* nn.Conv2d + folded BatchNorm (+ residual, + ReLU) as in deva/model/resnet.py:46-114, group_modules.py:41-67,
+ * modules.py:22-39; `desc` is a HOST struct. */
+DEVA_B200_API int deva_b200_conv2d(const deva_b200_conv_desc* desc, deva_stream_t stream);
+/* 7x7 stride-2 stem conv + BN + ReLU (resnet.py:120-122) on the 4-channel bordered input made by
+ * deva_b200_stem_input: x fp16 [batch, h+6, w+6, 4], w_packed fp16 [64, 256], out fp16 NHWC [batch, h/2, w/2, 64]. */
+DEVA_B200_API int deva_b200_stem_conv(const void* x, int batch, int h, int w, const void* w_packed, const float* bias,
+                                      void* out_relu, int th, int tw, deva_stream_t stream);
+DEVA_B200_API int deva_b200_stem_input(const float* image, const float* masks, void* dst, int k, int h, int w,
+                                       deva_stream_t stream);
+DEVA_B200_API int deva_b200_nchw_to_nhwc(const float* src, void* dst, int b, int c, int h, int w, int c_pad,
+                                         deva_stream_t stream);
+DEVA_B200_API int deva_b200_nhwc_to_nchw(const void* src, float* dst, int b, int c, int h, int w, deva_stream_t stream);
+/* 3x3 stride-2 max pool (resnet.py:123) */
+DEVA_B200_API int deva_b200_maxpool(const void* x, void* y, int b, int h, int w, int c, deva_stream_t stream);
+/* bilinear x2 (align_corners=False) + broadcast skip add -> raw and/or ReLU'd (modules.py:88-91) */
+DEVA_B200_API int deva_b200_up2_add(const void* g, const void* skip, void* raw, void* relu, int b, int h, int w, int c,
+                                    deva_stream_t stream);
+/* F.interpolate(mode='area') by an integer ratio r (group_modules.py:33-38), fp16 NHWC and fp32 planes */
+DEVA_B200_API int deva_b200_area_down(const void* x, void* y, int b, int h, int w, int c, int r, deva_stream_t stream);
+DEVA_B200_API int deva_b200_area_down_plane(const float* x, float* y, int b, int h, int w, int r, deva_stream_t stream);
+/* x + CBAM(x) (cbam.py:21-77 inside group_modules.py:146-150); scratch: fp32 [3*b*c + 2*b*h*w] */
+DEVA_B200_API int deva_b200_cbam(const void* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                                 const float* ws, const float* bs, float* scratch, void* raw, void* relu, int b, int h,
+                                 int w, int c, int r, deva_stream_t stream);
+/* sensory GRU gates (modules.py:145-149): values fp16 [pixels, 3c], h fp16 [pixels, c] -> out fp16 */
+DEVA_B200_API int deva_b200_gru(const void* values, const void* h, void* out, int64_t pixels, int c,
+                                deva_stream_t stream);
+/* key projection tail (modules.py:73-78): y fp32 [q, ld] = [key | d | e] -> key [q,ck], shrinkage [q], selection [q,ck] */
+DEVA_B200_API int deva_b200_key_tail(const float* y, int ld, int q, int ck, float* key, float* shrinkage,
+                                     float* selection, deva_stream_t stream);
+/* sigmoid -> aggregate -> bilinear x4 -> softmax (network.py:33-40,144-168): logits fp32 [k,h,w] ->
+ * prob fp32 [(k+1),4h,4w] (and optionally the up-sampled logits); agg: fp32 scratch [(k+1),h,w] */
+DEVA_B200_API int deva_b200_output_tail(const float* logits, float* agg, float* prob, float* logits_out, int k, int h,
+                                        int w, deva_stream_t stream);
+/* fp16 token-major values [n, c] -> bank rows dst[c, j] (ld_dst): append from the NHWC value encoder */
+DEVA_B200_API int deva_b200_transpose_append(const void* src, void* dst, int64_t ld_dst, int n, int c,
+                                             deva_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,8 @@
 
 #include "bank_ops.h"
 #include "common.h"
+#include "conv.h"
+#include "elementwise.h"
 #include "readout.h"
 #include "simtopk.h"
 
@@ -62,9 +64,10 @@ DEVA_B200_API int deva_b200_sim_dense_softmax(const void* k_hi, const void* k_lo
 }
 DEVA_B200_API int deva_b200_readout(const void* values, int64_t values_ld, int64_t values_rows, const int32_t* val_row,
                       const int32_t* out_row, int n_groups, int rows_per_group, const void* affinity,
-                      int64_t ld_affinity, int n_window, int q, float* out, int64_t ld_out, deva_stream_t stream) {
+                      int64_t ld_affinity, int n_window, int q, float* out, int64_t ld_out, void* out_tok,
+                      deva_stream_t stream) {
   return launch_readout(H(values), values_ld, values_rows, val_row, out_row, n_groups, rows_per_group, H(affinity),
-                        ld_affinity, n_window, q, out, ld_out, S(stream));
+                        ld_affinity, n_window, q, out, ld_out, H(out_tok), S(stream));
 }
 DEVA_B200_API int deva_b200_gather_rows(void* dst, const void* src, const int32_t* idx, int n, int row_bytes, deva_stream_t stream) {
   return launch_gather_rows(dst, src, idx, n, row_bytes, S(stream));
@@ -78,6 +81,66 @@ DEVA_B200_API int deva_b200_gather_cols_f16(void* dst, int64_t ld_dst, const voi
 }
 DEVA_B200_API int deva_b200_usage(float* out, const float* use_cnt, const float* life_cnt, int n, deva_stream_t stream) {
   return launch_usage(out, use_cnt, life_cnt, n, S(stream));
+}
+
+DEVA_B200_API int deva_b200_conv2d(const deva_b200_conv_desc* c, deva_stream_t stream) {
+  ConvDesc d;
+  d.x = c->x; d.batch = c->batch; d.h = c->h; d.w = c->w; d.cin_pad = c->cin_pad;
+  d.w_packed = c->w_packed; d.kh = c->kh; d.kw = c->kw; d.stride = c->stride;
+  d.cout = c->cout; d.cout_pad = c->cout_pad; d.nt = c->nt; d.th = c->th; d.tw = c->tw;
+  d.bias = c->bias; d.res = c->res; d.res_broadcast = c->res_broadcast;
+  d.rank1_w = c->rank1_w; d.rank1_x = c->rank1_x;
+  d.out_raw = c->out_raw; d.out_relu = c->out_relu; d.out_f32 = c->out_f32;
+  return launch_conv(d, S(stream));
+}
+DEVA_B200_API int deva_b200_stem_conv(const void* x, int batch, int h, int w, const void* w_packed, const float* bias,
+                                      void* out_relu, int th, int tw, deva_stream_t stream) {
+  return launch_stem(x, batch, h, w, w_packed, bias, out_relu, th, tw, S(stream));
+}
+DEVA_B200_API int deva_b200_stem_input(const float* image, const float* masks, void* dst, int k, int h, int w,
+                                       deva_stream_t stream) {
+  return ew_stem_input(image, masks, H(dst), k, h, w, S(stream));
+}
+DEVA_B200_API int deva_b200_nchw_to_nhwc(const float* src, void* dst, int b, int c, int h, int w, int c_pad,
+                                         deva_stream_t stream) {
+  return ew_nchw_to_nhwc(src, H(dst), b, c, h, w, c_pad, S(stream));
+}
+DEVA_B200_API int deva_b200_nhwc_to_nchw(const void* src, float* dst, int b, int c, int h, int w, deva_stream_t stream) {
+  return ew_nhwc_to_nchw(H(src), dst, b, c, h, w, S(stream));
+}
+DEVA_B200_API int deva_b200_maxpool(const void* x, void* y, int b, int h, int w, int c, deva_stream_t stream) {
+  return ew_maxpool(H(x), H(y), b, h, w, c, S(stream));
+}
+DEVA_B200_API int deva_b200_up2_add(const void* g, const void* skip, void* raw, void* relu, int b, int h, int w, int c,
+                                    deva_stream_t stream) {
+  return ew_up2_add(H(g), H(skip), H(raw), H(relu), b, h, w, c, S(stream));
+}
+DEVA_B200_API int deva_b200_area_down(const void* x, void* y, int b, int h, int w, int c, int r, deva_stream_t stream) {
+  return ew_area_down(H(x), H(y), b, h, w, c, r, S(stream));
+}
+DEVA_B200_API int deva_b200_area_down_plane(const float* x, float* y, int b, int h, int w, int r, deva_stream_t stream) {
+  return ew_area_down_plane(x, y, b, h, w, r, S(stream));
+}
+DEVA_B200_API int deva_b200_cbam(const void* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                                 const float* ws, const float* bs, float* scratch, void* raw, void* relu, int b, int h,
+                                 int w, int c, int r, deva_stream_t stream) {
+  return ew_cbam(H(x), w1, b1, w2, b2, ws, bs, scratch, H(raw), H(relu), b, h, w, c, r, S(stream));
+}
+DEVA_B200_API int deva_b200_gru(const void* values, const void* h, void* out, int64_t pixels, int c,
+                                deva_stream_t stream) {
+  return ew_gru(H(values), H(h), H(out), pixels, c, S(stream));
+}
+DEVA_B200_API int deva_b200_key_tail(const float* y, int ld, int q, int ck, float* key, float* shrinkage,
+                                     float* selection, deva_stream_t stream) {
+  return ew_key_tail(y, ld, q, ck, key, shrinkage, selection, S(stream));
+}
+DEVA_B200_API int deva_b200_output_tail(const float* logits, float* agg, float* prob, float* logits_out, int k, int h,
+                                        int w, deva_stream_t stream) {
+  return ew_output_tail(logits, agg, prob, logits_out, k, h, w, S(stream));
+}
+DEVA_B200_API int deva_b200_transpose_append(const void* src, void* dst, int64_t ld_dst, int n, int c,
+                                             deva_stream_t stream) {
+  return ew_transpose_append(H(src), H(dst), ld_dst, n, c, S(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,454 @@
+// HBM-bound helper kernels of the NHWC fp16 network path: layout/precision conversion at the API boundary,
+// max-pool, bilinear x2 + skip add, area down-sampling, CBAM (reference deva/model/cbam.py:21-77), the
+// non-standard sensory GRU (modules.py:145-149), and the soft-aggregation / x4 upsampling / softmax tail
+// (network.py:33-40,144-168).  One thread per output element (or per pixel x channel-vector); all accesses
+// are coalesced along the channel axis.
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include "common.h"
+#include "elementwise.h"
+
+namespace b200 {
+namespace ew {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---------------------------------------------------------------- layout conversion
+// fp32 NCHW [B,C,H,W] -> fp16 NHWC [B,H,W,Cp] (channels >= C are zero)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __half* __restrict__ dst, int B, int C, int H, int W,
+                                    int Cp) {
+  const long long total = (long long)B * H * W * Cp;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % Cp);
+    long long p = i / Cp;
+    const int x = (int)(p % W); p /= W;
+    const int y = (int)(p % H);
+    const int b = (int)(p / H);
+    dst[i] = (c < C) ? __float2half_rn(src[(((long long)b * C + c) * H + y) * W + x]) : __float2half_rn(0.f);
+  }
+}
+// fp16 NHWC [B,H,W,C] -> fp32 NCHW [B,C,H,W]
+__global__ void nhwc_to_nchw_kernel(const __half* __restrict__ src, float* __restrict__ dst, int B, int C, int H, int W) {
+  const long long total = (long long)B * C * H * W;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int x = (int)(i % W);
+    long long p = i / W;
+    const int y = (int)(p % H); p /= H;
+    const int c = (int)(p % C);
+    const int b = (int)(p / C);
+    dst[i] = __half2float(src[(((long long)b * H + y) * W + x) * C + c]);
+  }
+}
+// Stem input: image fp32 [3,H,W] (+ optional per-object mask fp32 [K,H,W]) -> fp16 [K, H+6, W+6, 4]
+// with a 3-pixel zero border (the 7x7 stride-2 padding) and channel 3 = mask (or 0).
+__global__ void stem_input_kernel(const float* __restrict__ image, const float* __restrict__ masks,
+                                  __half* __restrict__ dst, int K, int H, int W) {
+  const int Hp = H + 6, Wp = W + 6;
+  const long long total = (long long)K * Hp * Wp;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int xp = (int)(i % Wp);
+    long long p = i / Wp;
+    const int yp = (int)(p % Hp);
+    const int k = (int)(p / Hp);
+    const int x = xp - 3, y = yp - 3;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (x >= 0 && x < W && y >= 0 && y < H) {
+      const long long o = (long long)y * W + x;
+      v[0] = image[o]; v[1] = image[(long long)H * W + o]; v[2] = image[2ll * H * W + o];
+      if (masks) v[3] = masks[(long long)k * H * W + o];
+    }
+    __half2* d = reinterpret_cast<__half2*>(dst + i * 4);
+    d[0] = __floats2half2_rn(v[0], v[1]);
+    d[1] = __floats2half2_rn(v[2], v[3]);
+  }
+}
+
+// ---------------------------------------------------------------- pooling / resampling (NHWC fp16, 8 channels per thread)
+__device__ __forceinline__ void ld8(const __half* p, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { const float2 t = __half22float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+}
+__device__ __forceinline__ void st8(__half* p, const float (&f)[8], bool relu) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    h[e] = relu ? __floats2half2_rn(fmaxf(f[2 * e], 0.f), fmaxf(f[2 * e + 1], 0.f)) : __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+
+// 3x3 stride-2 pad-1 max pool (resnet.py:123)
+__global__ void maxpool_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, C8 = C / 8;
+  const long long total = (long long)B * Ho * Wo * C8;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % C8) * 8;
+    long long p = i / C8;
+    const int xo = (int)(p % Wo); p /= Wo;
+    const int yo = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -CUDART_INF_F;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = 2 * yo + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = 2 * xo + dx;
+        if (xx < 0 || xx >= W) continue;
+        float f[8];
+        ld8(x + (((long long)b * H + yy) * W + xx) * C + c, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], f[e]);
+      }
+    }
+    st8(y + (((long long)b * Ho + yo) * Wo + xo) * C + c, m, false);
+  }
+}
+
+// out = bilinear_x2(g) + skip (skip is one image broadcast over the batch); writes raw and/or relu
+// (MaskUpsampleBlock: upsample_groups + distributor 'add', modules.py:88-91)
+__global__ void up2_add_kernel(const __half* __restrict__ g, const __half* __restrict__ skip, __half* __restrict__ raw,
+                               __half* __restrict__ relu, int B, int h, int w, int C) {
+  const int H = 2 * h, W = 2 * w, C8 = C / 8;
+  const long long total = (long long)B * H * W * C8;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % C8) * 8;
+    long long p = i / C8;
+    const int X = (int)(p % W); p /= W;
+    const int Y = (int)(p % H);
+    const int b = (int)(p / H);
+    // align_corners=False: src = (dst + 0.5)/2 - 0.5, clamped at 0
+    const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float wy = sy - y0, wx = sx - x0;
+    float a[8], bq[8], cq[8], d[8], o[8], s[8];
+    const __half* gb = g + (long long)b * h * w * C + c;
+    ld8(gb + ((long long)y0 * w + x0) * C, a);
+    ld8(gb + ((long long)y0 * w + x1) * C, bq);
+    ld8(gb + ((long long)y1 * w + x0) * C, cq);
+    ld8(gb + ((long long)y1 * w + x1) * C, d);
+    ld8(skip + ((long long)Y * W + X) * C + c, s);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float top = a[e] + (bq[e] - a[e]) * wx, bot = cq[e] + (d[e] - cq[e]) * wx;
+      o[e] = top + (bot - top) * wy + s[e];
+    }
+    const long long off = (((long long)b * H + Y) * W + X) * C + c;
+    if (raw) st8(raw + off, o, false);
+    if (relu) st8(relu + off, o, true);
+  }
+}
+
+// r x r average pooling (F.interpolate mode='area' with an integer ratio), NHWC fp16
+__global__ void area_down_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C, int r) {
+  const int Ho = H / r, Wo = W / r, C8 = C / 8;
+  const long long total = (long long)B * Ho * Wo * C8;
+  const float inv = 1.f / (r * r);
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % C8) * 8;
+    long long p = i / C8;
+    const int xo = (int)(p % Wo); p /= Wo;
+    const int yo = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int dy = 0; dy < r; ++dy)
+      for (int dx = 0; dx < r; ++dx) {
+        float f[8];
+        ld8(x + (((long long)b * H + yo * r + dy) * W + xo * r + dx) * C + c, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= inv;
+    st8(y + (((long long)b * Ho + yo) * Wo + xo) * C + c, acc, false);
+  }
+}
+// same for single-channel fp32 planes [B,H,W] -> [B,H/r,W/r]
+__global__ void area_down_plane_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int r) {
+  const int Ho = H / r, Wo = W / r;
+  const long long total = (long long)B * Ho * Wo;
+  const float inv = 1.f / (r * r);
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int xo = (int)(i % Wo);
+    long long p = i / Wo;
+    const int yo = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float acc = 0.f;
+    for (int dy = 0; dy < r; ++dy)
+      for (int dx = 0; dx < r; ++dx) acc += x[((long long)b * H + yo * r + dy) * W + xo * r + dx];
+    y[i] = acc * inv;
+  }
+}
+
+// ---------------------------------------------------------------- CBAM (cbam.py:21-77)
+// per (image, channel) mean and max over the pixels.  grid = (B, C/256... ) one thread per channel.
+__global__ void cbam_pool_kernel(const __half* __restrict__ x, float* __restrict__ avg, float* __restrict__ mx, int HW, int C) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const __half* p = x + (long long)b * HW * C + c;
+  float s = 0.f, m = -CUDART_INF_F;
+  for (int i = 0; i < HW; ++i) {
+    const float v = __half2float(p[(long long)i * C]);
+    s += v;
+    m = fmaxf(m, v);
+  }
+  avg[b * C + c] = s / HW;
+  mx[b * C + c] = m;
+}
+// gate[b,c] = sigmoid(mlp(avg) + mlp(max)), mlp = Linear(C,R) -> ReLU -> Linear(R,C); one block per image
+__global__ void cbam_mlp_kernel(const float* __restrict__ avg, const float* __restrict__ mx, const float* __restrict__ w1,
+                                const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                                float* __restrict__ gate, int C, int R) {
+  extern __shared__ float hid[];  // [2][R]
+  const int b = blockIdx.x;
+  for (int r = threadIdx.x; r < 2 * R; r += blockDim.x) {
+    const float* src = (r < R ? avg : mx) + b * C;
+    const float* wr = w1 + (long long)(r % R) * C;
+    float a = b1[r % R];
+    for (int c = 0; c < C; ++c) a += wr[c] * src[c];
+    hid[r] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 2.f * b2[c];
+    for (int r = 0; r < R; ++r) a += w2[(long long)c * R + r] * (hid[r] + hid[R + r]);
+    gate[b * C + c] = sigmoidf_(a);
+  }
+}
+// per pixel: max and mean over channels of x * gate -> stats [B,HW,2]; one warp per pixel
+__global__ void cbam_stats_kernel(const __half* __restrict__ x, const float* __restrict__ gate, float* __restrict__ stats,
+                                  int B, int HW, int C) {
+  const long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pix >= (long long)B * HW) return;
+  const int b = (int)(pix / HW);
+  const __half* p = x + pix * C;
+  const float* g = gate + b * C;
+  float s = 0.f, m = -CUDART_INF_F;
+  for (int c = lane; c < C; c += 32) {
+    const float v = __half2float(p[c]) * g[c];
+    s += v;
+    m = fmaxf(m, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+  if (lane == 0) { stats[pix * 2] = m; stats[pix * 2 + 1] = s / C; }
+}
+// out = x + x * gate * sigmoid(conv7x7(stats))   (FeatureFusion: g + attention(g)); one warp per pixel
+__global__ void cbam_apply_kernel(const __half* __restrict__ x, const float* __restrict__ gate, const float* __restrict__ stats,
+                                  const float* __restrict__ ws, const float* __restrict__ bs, __half* __restrict__ raw,
+                                  __half* __restrict__ relu, int B, int H, int W, int C) {
+  const long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pix >= (long long)B * H * W) return;
+  const int b = (int)(pix / ((long long)H * W));
+  const int rem = (int)(pix - (long long)b * H * W);
+  const int y = rem / W, xq = rem - y * W;
+  float a = 0.f;
+  for (int t = lane; t < 98; t += 32) {
+    const int ch = t / 49, k = t % 49, dy = k / 7 - 3, dx = k % 7 - 3;
+    const int yy = y + dy, xx = xq + dx;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) a += ws[t] * stats[(((long long)b * H + yy) * W + xx) * 2 + ch];
+  }
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  const float sg = sigmoidf_(a + bs[0]);
+  const float* g = gate + b * C;
+  for (int c = lane; c < C; c += 32) {
+    const float v = __half2float(x[pix * C + c]);
+    const float o = v + v * g[c] * sg;
+    if (raw) raw[pix * C + c] = __float2half_rn(o);
+    if (relu) relu[pix * C + c] = __float2half_rn(fmaxf(o, 0.f));
+  }
+}
+
+// ---------------------------------------------------------------- sensory GRU (modules.py:145-149, quirk Q7)
+// values fp16 NHWC [B,HW,3C] = [forget | update | new]; h fp16 [B,HW,C] -> h' = f*h*(1-u) + u*tanh(n)
+__global__ void gru_kernel(const __half* __restrict__ values, const __half* __restrict__ h, __half* __restrict__ out,
+                           long long pixels, int C) {
+  const long long total = pixels * C;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long p = i / C;
+    const int c = (int)(i - p * C);
+    const __half* v = values + p * 3 * C;
+    const float f = sigmoidf_(__half2float(v[c])), u = sigmoidf_(__half2float(v[C + c])), n = tanhf(__half2float(v[2 * C + c]));
+    const float hv = __half2float(h[i]);
+    out[i] = __float2half_rn(f * hv * (1.f - u) + u * n);
+  }
+}
+
+// ---------------------------------------------------------------- key projection tail (modules.py:73-78)
+// y fp32 [Q, ld] = [key(CK) | d(1) | e(CK)] -> key [Q,CK], shrinkage [Q] = d^2+1, selection [Q,CK] = sigmoid(e)
+__global__ void key_tail_kernel(const float* __restrict__ y, int ld, int Q, int CK, float* __restrict__ key,
+                                float* __restrict__ shr, float* __restrict__ sel) {
+  const long long total = (long long)Q * CK;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long q = i / CK;
+    const int c = (int)(i - q * CK);
+    const float* row = y + q * ld;
+    key[i] = row[c];
+    sel[i] = sigmoidf_(row[CK + 1 + c]);
+    if (c == 0) shr[q] = row[CK] * row[CK] + 1.f;
+  }
+}
+
+// ---------------------------------------------------------------- output tail (network.py:33-40,144-168)
+// logits fp32 [K,h,w] (pred output) -> aggregated log-odds [(K+1),h,w]
+__global__ void aggregate_kernel(const float* __restrict__ logits, float* __restrict__ agg, int K, int HW) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= HW) return;
+  float bg = 1.f;
+  for (int k = 0; k < K; ++k) {
+    const float pk = sigmoidf_(logits[(long long)k * HW + i]);
+    bg *= (1.f - pk);
+    const float c = fminf(fmaxf(pk, 1e-7f), 1.f - 1e-7f);
+    agg[(long long)(k + 1) * HW + i] = logf(c / (1.f - c));
+  }
+  const float c = fminf(fmaxf(bg, 1e-7f), 1.f - 1e-7f);
+  agg[i] = logf(c / (1.f - c));
+}
+// bilinear x4 (align_corners=False) of agg [(K+1),h,w] + softmax over channels -> prob (and logits) [(K+1),4h,4w]
+__global__ void up4_softmax_kernel(const float* __restrict__ agg, float* __restrict__ prob, float* __restrict__ logits_out,
+                                   int K1, int h, int w) {
+  const int H = 4 * h, W = 4 * w;
+  const long long i = blockIdx.x * 256ll + threadIdx.x;
+  if (i >= (long long)H * W) return;
+  const int Y = (int)(i / W), X = (int)(i - (long long)Y * W);
+  const float sy = fmaxf((Y + 0.5f) * 0.25f - 0.5f, 0.f), sx = fmaxf((X + 0.5f) * 0.25f - 0.5f, 0.f);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float wy = sy - y0, wx = sx - x0;
+  const long long o00 = (long long)y0 * w + x0, o01 = (long long)y0 * w + x1, o10 = (long long)y1 * w + x0,
+                  o11 = (long long)y1 * w + x1;
+  float m = -CUDART_INF_F;
+  for (int k = 0; k < K1; ++k) {
+    const float* a = agg + (long long)k * h * w;
+    const float top = a[o00] + (a[o01] - a[o00]) * wx, bot = a[o10] + (a[o11] - a[o10]) * wx;
+    const float v = top + (bot - top) * wy;
+    prob[(long long)k * H * W + i] = v;  // stash the logit
+    if (logits_out) logits_out[(long long)k * H * W + i] = v;
+    m = fmaxf(m, v);
+  }
+  float s = 0.f;
+  for (int k = 0; k < K1; ++k) {
+    const float e = expf(prob[(long long)k * H * W + i] - m);
+    prob[(long long)k * H * W + i] = e;
+    s += e;
+  }
+  const float inv = 1.f / s;
+  for (int k = 0; k < K1; ++k) prob[(long long)k * H * W + i] *= inv;
+}
+
+// fp16 token-major [n, C] -> fp16 bank rows dst[c, j] (ld_dst): value append from the NHWC encoder output
+__global__ void transpose_append_kernel(const __half* __restrict__ src, __half* __restrict__ dst, long long ld_dst, int n,
+                                        int C) {
+  __shared__ __half tile[32][33];
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8)
+    tile[r][tx] = (n0 + r < n && c0 + tx < C) ? src[(long long)(n0 + r) * C + c0 + tx] : __float2half_rn(0.f);
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (c0 + r < C && n0 + tx < n) dst[(long long)(c0 + r) * ld_dst + n0 + tx] = tile[tx][r];
+}
+// fp32 [rows, Q] channel-major (readout GEMM output) -> fp16 NHWC-style [Q, rows]... not needed: the readout GEMM
+// writes token-major directly (see readout.cu).
+
+}  // namespace ew
+
+static int grid_of(long long total) {
+  long long g = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int ew_nchw_to_nhwc(const float* src, __half* dst, int B, int C, int H, int W, int Cp, cudaStream_t s) {
+  ew::nchw_to_nhwc_kernel<<<grid_of((long long)B * H * W * Cp), 256, 0, s>>>(src, dst, B, C, H, W, Cp);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_nhwc_to_nchw(const __half* src, float* dst, int B, int C, int H, int W, cudaStream_t s) {
+  ew::nhwc_to_nchw_kernel<<<grid_of((long long)B * C * H * W), 256, 0, s>>>(src, dst, B, C, H, W);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_stem_input(const float* image, const float* masks, __half* dst, int K, int H, int W, cudaStream_t s) {
+  ew::stem_input_kernel<<<grid_of((long long)K * (H + 6) * (W + 6)), 256, 0, s>>>(image, masks, dst, K, H, W);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_maxpool(const __half* x, __half* y, int B, int H, int W, int C, cudaStream_t s) {
+  B200_REQUIRE(C % 8 == 0, "maxpool: C %% 8");
+  ew::maxpool_kernel<<<grid_of((long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8)), 256, 0, s>>>(x, y, B, H, W, C);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_up2_add(const __half* g, const __half* skip, __half* raw, __half* relu, int B, int h, int w, int C, cudaStream_t s) {
+  B200_REQUIRE(C % 8 == 0, "up2_add: C %% 8");
+  ew::up2_add_kernel<<<grid_of((long long)B * 4 * h * w * (C / 8)), 256, 0, s>>>(g, skip, raw, relu, B, h, w, C);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_area_down(const __half* x, __half* y, int B, int H, int W, int C, int r, cudaStream_t s) {
+  B200_REQUIRE(C % 8 == 0 && H % r == 0 && W % r == 0, "area_down: shape");
+  ew::area_down_kernel<<<grid_of((long long)B * (H / r) * (W / r) * (C / 8)), 256, 0, s>>>(x, y, B, H, W, C, r);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_area_down_plane(const float* x, float* y, int B, int H, int W, int r, cudaStream_t s) {
+  B200_REQUIRE(H % r == 0 && W % r == 0, "area_down_plane: shape");
+  ew::area_down_plane_kernel<<<grid_of((long long)B * (H / r) * (W / r)), 256, 0, s>>>(x, y, B, H, W, r);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_cbam(const __half* x, const float* w1, const float* b1, const float* w2, const float* b2, const float* ws,
+            const float* bs, float* scratch, __half* raw, __half* relu, int B, int H, int W, int C, int R,
+            cudaStream_t s) {
+  // scratch: avg[B*C] | max[B*C] | gate[B*C] | stats[B*H*W*2]
+  float* avg = scratch;
+  float* mx = avg + (long long)B * C;
+  float* gate = mx + (long long)B * C;
+  float* stats = gate + (long long)B * C;
+  const int HW = H * W;
+  ew::cbam_pool_kernel<<<dim3(ceil_div(C, 128), B), 128, 0, s>>>(x, avg, mx, HW, C);
+  B200_LAUNCH_CHECK();
+  ew::cbam_mlp_kernel<<<B, 256, 2 * R * sizeof(float), s>>>(avg, mx, w1, b1, w2, b2, gate, C, R);
+  B200_LAUNCH_CHECK();
+  const long long warps = (long long)B * HW;
+  ew::cbam_stats_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, gate, stats, B, HW, C);
+  B200_LAUNCH_CHECK();
+  ew::cbam_apply_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, gate, stats, ws, bs, raw, relu, B, H, W, C);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_gru(const __half* values, const __half* h, __half* out, long long pixels, int C, cudaStream_t s) {
+  ew::gru_kernel<<<grid_of(pixels * C), 256, 0, s>>>(values, h, out, pixels, C);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_key_tail(const float* y, int ld, int Q, int CK, float* key, float* shr, float* sel, cudaStream_t s) {
+  ew::key_tail_kernel<<<grid_of((long long)Q * CK), 256, 0, s>>>(y, ld, Q, CK, key, shr, sel);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_output_tail(const float* logits, float* agg, float* prob, float* logits_out, int K, int h, int w, cudaStream_t s) {
+  ew::aggregate_kernel<<<ceil_div(h * w, 256), 256, 0, s>>>(logits, agg, K, h * w);
+  B200_LAUNCH_CHECK();
+  ew::up4_softmax_kernel<<<ceil_div(16ll * h * w, 256), 256, 0, s>>>(agg, prob, logits_out, K + 1, h, w);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_transpose_append(const __half* src, __half* dst, long long ld_dst, int n, int C, cudaStream_t s) {
+  ew::transpose_append_kernel<<<dim3(ceil_div(n, 32), ceil_div(C, 32)), 256, 0, s>>>(src, dst, ld_dst, n, C);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,20 @@
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace b200 {
+int ew_nchw_to_nhwc(const float* src, __half* dst, int B, int C, int H, int W, int Cp, cudaStream_t s);
+int ew_nhwc_to_nchw(const __half* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
+int ew_stem_input(const float* image, const float* masks, __half* dst, int K, int H, int W, cudaStream_t s);
+int ew_maxpool(const __half* x, __half* y, int B, int H, int W, int C, cudaStream_t s);
+int ew_up2_add(const __half* g, const __half* skip, __half* raw, __half* relu, int B, int h, int w, int C, cudaStream_t s);
+int ew_area_down(const __half* x, __half* y, int B, int H, int W, int C, int r, cudaStream_t s);
+int ew_area_down_plane(const float* x, float* y, int B, int H, int W, int r, cudaStream_t s);
+int ew_cbam(const __half* x, const float* w1, const float* b1, const float* w2, const float* b2, const float* ws,
+            const float* bs, float* scratch, __half* raw, __half* relu, int B, int H, int W, int C, int R,
+            cudaStream_t s);
+int ew_gru(const __half* values, const __half* h, __half* out, long long pixels, int C, cudaStream_t s);
+int ew_key_tail(const float* y, int ld, int Q, int CK, float* key, float* shr, float* sel, cudaStream_t s);
+int ew_output_tail(const float* logits, float* agg, float* prob, float* logits_out, int K, int h, int w, cudaStream_t s);
+int ew_transpose_append(const __half* src, __half* dst, long long ld_dst, int n, int C, cudaStream_t s);
+}  // namespace b200

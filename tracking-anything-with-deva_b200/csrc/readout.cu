@@ -33,6 +33,8 @@ struct Params {
   int q;
   long long ldo;
   float* out;
+  __half* out_tok;  // optional fp16 token-major output [object, q, rows_per_group]
+  int rows_per_group;
   int val_row[kMaxGroups];
   int out_row[kMaxGroups];
 };
@@ -149,7 +151,15 @@ readout_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_constant_
         tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + c * 32, r);
         tmem_ld_wait();
         const int q0 = n * BN + c * 32;
-        if (q0 + 32 <= p.q && vec_ok) {
+        if (p.out_tok) {
+          const long long R = p.out_row[g] + (long long)(m - g * p.tiles_per_group) * BM + row;
+          const long long obj = R / p.rows_per_group;
+          const int ch = (int)(R - obj * p.rows_per_group);
+          __half* dt = p.out_tok + (obj * p.q) * p.rows_per_group + ch;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (q0 + j < p.q) dt[(long long)(q0 + j) * p.rows_per_group] = __float2half_rn(__uint_as_float(r[j]));
+        } else if (q0 + 32 <= p.q && vec_ok) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
@@ -180,7 +190,7 @@ readout_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_constant_
 
 int launch_readout(const __half* values, long long values_ld, long long values_rows, const int* val_row,
                    const int* out_row, int n_groups, int rows_per_group, const __half* P, long long ldP,
-                   int n_window, int q, float* out, long long ldo, cudaStream_t stream) {
+                   int n_window, int q, float* out, long long ldo, __half* out_tok, cudaStream_t stream) {
   using namespace readout;
   B200_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups, "readout: n_groups %d out of range [1,%d]", n_groups,
                kMaxGroups);
@@ -202,6 +212,8 @@ int launch_readout(const __half* values, long long values_ld, long long values_r
   p.q = q;
   p.ldo = ldo;
   p.out = out;
+  p.out_tok = out_tok;
+  p.rows_per_group = rows_per_group;
   for (int i = 0; i < n_groups; ++i) {
     p.val_row[i] = val_row[i];
     p.out_row[i] = out_row[i];

@@ -9,5 +9,6 @@ constexpr int kMaxGroups = 256;  // objects per readout launch
 // for g < n_groups, r < rows_per_group, q < q, n < n_window.  val_row/out_row are HOST arrays.
 int launch_readout(const __half* values, long long values_ld, long long values_rows, const int* val_row,
                    const int* out_row, int n_groups, int rows_per_group, const __half* P, long long ldP,
-                   int n_window, int q, float* out, long long ldo, cudaStream_t stream);
+                   int n_window, int q, float* out, long long ldo, __half* out_tok, cudaStream_t stream);
+// out_tok (optional, replaces `out`): fp16 token-major [object, q, rows_per_group] with object = out_row / rows_per_group
 }  // namespace b200

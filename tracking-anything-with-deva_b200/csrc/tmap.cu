@@ -60,29 +60,40 @@ int make_tmap_2d(CUtensorMap* out, TmapType type, const void* base, uint64_t inn
   return 0;
 }
 
-int make_tmap_nhwc(CUtensorMap* out, TmapType type, const void* base, uint64_t c, uint64_t w, uint64_t h,
-                   uint64_t n, uint32_t box_c, uint32_t box_w, uint32_t box_h, const char** err) {
+int make_tmap_f16_5d(CUtensorMap* out, const void* base, const uint64_t (&dims)[5], const long long (&strides)[4],
+                     const uint32_t (&box)[5], const char** err) {
   EncodeTiledFn fn = resolve_encode(err);
   if (!fn) return 1;
-  uint32_t esize;
-  CUtensorMapDataType dt = to_cu(type, &esize);
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((c * esize) & 15) || box_c * esize != 128 || box_w > 256 ||
-      box_h > 256) {
-    if (err) *err = "make_tmap_nhwc: bad alignment / box";
+  bool bad = (reinterpret_cast<uintptr_t>(base) & 15) != 0 || box[0] * 2 > 128;
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t bx[5], estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 5; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; bad |= dims[i] == 0 || box[i] == 0 || box[i] > 256; }
+  for (int i = 0; i < 4; ++i) { gstride[i] = (cuuint64_t)strides[i] * 2; bad |= (strides[i] & 7) != 0 || strides[i] <= 0; }
+  if (bad) {
+    if (err) *err = "make_tmap_f16_5d: bad alignment / box";
     return 2;
   }
-  cuuint64_t gdim[4] = {c, w, h, n};
-  cuuint64_t gstride[3] = {c * esize, c * esize * w, c * esize * w * h};
-  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(out, dt, 4, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), gdim, gstride, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    if (err) *err = "cuTensorMapEncodeTiled(4d) failed";
+    if (err) *err = "cuTensorMapEncodeTiled(5d) failed";
     return 3;
   }
   return 0;
+}
+
+int make_tmap_act5(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t b,
+                   long long stride_w, long long stride_h, long long stride_b, uint32_t box_w, uint32_t box_h,
+                   const char** err) {
+  if (c < 64) {
+    if (err) *err = "make_tmap_act5: needs >= 64 channels";
+    return 2;
+  }
+  const uint64_t dims[5] = {c, w, h, b, 1};
+  const long long strides[4] = {stride_w, stride_h, stride_b, stride_b * (long long)b};
+  const uint32_t box[5] = {64, box_w, box_h, 1, 1};
+  return make_tmap_f16_5d(out, base, dims, strides, box, err);
 }
 
 }  // namespace b200

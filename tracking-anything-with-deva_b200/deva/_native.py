@@ -12,11 +12,22 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libdeva_b200.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 LIST_PITCH = 32
 MAX_GROUPS = 256
 
 _lib = None
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of ``deva_b200_conv_desc`` (include/deva_b200.h)."""
+    _fields_ = [('x', c_void_p), ('batch', c_int32), ('h', c_int32), ('w', c_int32), ('cin_pad', c_int32),
+                ('w_packed', c_void_p), ('kh', c_int32), ('kw', c_int32), ('stride', c_int32),
+                ('cout', c_int32), ('cout_pad', c_int32), ('nt', c_int32), ('th', c_int32), ('tw', c_int32),
+                ('bias', c_void_p), ('res', c_void_p), ('res_broadcast', c_int32),
+                ('rank1_w', c_void_p), ('rank1_x', c_void_p),
+                ('out_raw', c_void_p), ('out_relu', c_void_p), ('out_f32', c_void_p)]
+
 
 _SIGNATURES = {
     'deva_b200_abi_version': (c_int, []),
@@ -36,11 +47,26 @@ _SIGNATURES = {
                                             c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                             c_void_p]),
     'deva_b200_readout': (c_int, [c_void_p, c_int64, c_int64, POINTER(c_int32), POINTER(c_int32), c_int, c_int,
-                                  c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p]),
+                                  c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     'deva_b200_gather_rows': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'deva_b200_gather_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'deva_b200_gather_cols_f16': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     'deva_b200_usage': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    'deva_b200_conv2d': (c_int, [POINTER(ConvDesc), c_void_p]),
+    'deva_b200_stem_conv': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'deva_b200_stem_input': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'deva_b200_nchw_to_nhwc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'deva_b200_nhwc_to_nchw': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'deva_b200_maxpool': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'deva_b200_up2_add': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'deva_b200_area_down': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'deva_b200_area_down_plane': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'deva_b200_cbam': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'deva_b200_gru': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'deva_b200_key_tail': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'deva_b200_output_tail': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'deva_b200_transpose_append': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES.keys())
 
@@ -130,14 +156,14 @@ def sim_dense_softmax(k_hi, k_lo, neg_s, shrinkage, n_window, n_lead, q_hi, q_lo
 
 
 def readout(values, values_ld, values_rows, val_row, out_row, rows_per_group, affinity, ld_affinity, n_window, q,
-            out, ld_out):
+            out, ld_out, out_tok=None):
     n = len(val_row)
     assert n == len(out_row)
     arr_v = (c_int32 * n)(*val_row)
     arr_o = (c_int32 * n)(*out_row)
     _check(lib().deva_b200_readout(_ptr(values), values_ld, values_rows, arr_v, arr_o, n, rows_per_group,
-                                   _ptr(affinity), ld_affinity, n_window, q, _ptr(out), ld_out, _stream()),
-           'readout')
+                                   _ptr(affinity), ld_affinity, n_window, q, _ptr(out), ld_out, _ptr(out_tok),
+                                   _stream()), 'readout')
 
 
 def gather_rows(dst, src, idx, n, row_bytes):
@@ -155,3 +181,70 @@ def gather_cols_f16(dst, ld_dst, src, ld_src, idx, rows, n):
 
 def usage(out, use_cnt, life_cnt, n):
     _check(lib().deva_b200_usage(_ptr(out), _ptr(use_cnt), _ptr(life_cnt), n, _stream()), 'usage')
+
+
+# ------------------------------------------------------------------------------------------ network path
+def conv2d(x, batch, h, w, cin_pad, w_packed, kh, stride, cout, cout_pad, nt, th, tw, bias, res=None,
+           res_broadcast=False, rank1_w=None, rank1_x=None, out_raw=None, out_relu=None, out_f32=None):
+    d = ConvDesc(x.data_ptr(), batch, h, w, cin_pad, w_packed.data_ptr(), kh, kh, stride, cout, cout_pad, nt, th, tw,
+                 bias.data_ptr(), None if res is None else res.data_ptr(), int(res_broadcast),
+                 None if rank1_w is None else rank1_w.data_ptr(), None if rank1_x is None else rank1_x.data_ptr(),
+                 None if out_raw is None else out_raw.data_ptr(), None if out_relu is None else out_relu.data_ptr(),
+                 None if out_f32 is None else out_f32.data_ptr())
+    _check(lib().deva_b200_conv2d(ctypes.byref(d), _stream()), 'conv2d')
+
+
+def stem_conv(x, batch, h, w, w_packed, bias, out_relu, th, tw):
+    _check(lib().deva_b200_stem_conv(_ptr(x), batch, h, w, _ptr(w_packed), _ptr(bias), _ptr(out_relu), th, tw,
+                                     _stream()), 'stem_conv')
+
+
+def stem_input(image, masks, dst, k, h, w):
+    _check(lib().deva_b200_stem_input(_ptr(image), _ptr(masks), _ptr(dst), k, h, w, _stream()), 'stem_input')
+
+
+def nchw_to_nhwc(src, dst, b, c, h, w, c_pad):
+    _check(lib().deva_b200_nchw_to_nhwc(_ptr(src), _ptr(dst), b, c, h, w, c_pad, _stream()), 'nchw_to_nhwc')
+
+
+def nhwc_to_nchw(src, dst, b, c, h, w):
+    _check(lib().deva_b200_nhwc_to_nchw(_ptr(src), _ptr(dst), b, c, h, w, _stream()), 'nhwc_to_nchw')
+
+
+def maxpool(x, y, b, h, w, c):
+    _check(lib().deva_b200_maxpool(_ptr(x), _ptr(y), b, h, w, c, _stream()), 'maxpool')
+
+
+def up2_add(g, skip, raw, relu, b, h, w, c):
+    _check(lib().deva_b200_up2_add(_ptr(g), _ptr(skip), _ptr(raw), _ptr(relu), b, h, w, c, _stream()), 'up2_add')
+
+
+def area_down(x, y, b, h, w, c, r):
+    _check(lib().deva_b200_area_down(_ptr(x), _ptr(y), b, h, w, c, r, _stream()), 'area_down')
+
+
+def area_down_plane(x, y, b, h, w, r):
+    _check(lib().deva_b200_area_down_plane(_ptr(x), _ptr(y), b, h, w, r, _stream()), 'area_down_plane')
+
+
+def cbam(x, w1, b1, w2, b2, ws, bs, scratch, raw, relu, b, h, w, c, r):
+    _check(lib().deva_b200_cbam(_ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(ws), _ptr(bs), _ptr(scratch),
+                                _ptr(raw), _ptr(relu), b, h, w, c, r, _stream()), 'cbam')
+
+
+def gru(values, h, out, pixels, c):
+    _check(lib().deva_b200_gru(_ptr(values), _ptr(h), _ptr(out), pixels, c, _stream()), 'gru')
+
+
+def key_tail(y, ld, q, ck, key, shrinkage, selection):
+    _check(lib().deva_b200_key_tail(_ptr(y), ld, q, ck, _ptr(key), _ptr(shrinkage), _ptr(selection), _stream()),
+           'key_tail')
+
+
+def output_tail(logits, agg, prob, logits_out, k, h, w):
+    _check(lib().deva_b200_output_tail(_ptr(logits), _ptr(agg), _ptr(prob), _ptr(logits_out), k, h, w, _stream()),
+           'output_tail')
+
+
+def transpose_append(src, dst, ld_dst, n, c):
+    _check(lib().deva_b200_transpose_append(_ptr(src), _ptr(dst), ld_dst, n, c, _stream()), 'transpose_append')

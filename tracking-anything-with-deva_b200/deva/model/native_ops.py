@@ -1,0 +1,165 @@
+"""Host-side wrappers of the sm_100a network kernels: weight packing, tile choice, op calls.
+
+Activations are fp16 NHWC torch tensors [B, H, W, C]; weights are packed once per checkpoint into the
+layout the implicit-GEMM kernel streams with TMA ([Cout_pad, taps * Cin_pad] fp16, BN folded bias fp32).
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from deva import _native as nat
+
+_TILES = ((1, 128), (2, 64), (4, 32), (8, 16), (16, 8), (32, 4))
+
+
+def choose_tile(ho: int, wo: int) -> Tuple[int, int]:
+    """(th, tw) with th*tw = 128 that wastes the fewest MMA rows on an ho x wo output."""
+    best, best_cost = None, None
+    for th, tw in _TILES:
+        cost = -(-ho // th) * th * (-(-wo // tw) * tw)
+        if best_cost is None or cost < best_cost or (cost == best_cost and tw > best[1]):
+            best, best_cost = (th, tw), cost
+    return best
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class PackedConv:
+    """One convolution ready for ``deva_b200_conv2d``."""
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int,
+                 rank1_in: Optional[int] = None):
+        """weight [Cout, Cin, k, k] fp32 (BN folded); if ``rank1_in`` is given, that input channel is split
+        off as a rank-1 term (out += w[:, rank1_in] * x1) - used for the '+1' mask / logit channels."""
+        cout, cin, kh, kw = weight.shape
+        assert kh == kw and kh in (1, 3)
+        dev = weight.device
+        self.rank1_w = None
+        if rank1_in is not None:
+            assert kh == 1
+            keep = [c for c in range(cin) if c != rank1_in]
+            r1 = weight[:, rank1_in, 0, 0].float()
+            weight = weight[:, keep]
+            cin -= 1
+        self.cout, self.cin, self.k, self.stride = cout, cin, kh, stride
+        self.cin_pad = _round_up(cin, 64)
+        if cout >= 256:
+            self.nt = 256 if cout % 256 == 0 else (128 if cout % 128 == 0 else 0)
+        else:
+            self.nt = _round_up(cout, 32)
+        if self.nt == 0:
+            self.nt = 256
+        self.cout_pad = _round_up(cout, self.nt)
+        w = torch.zeros(self.cout_pad, kh * kw, self.cin_pad, dtype=torch.float32, device=dev)
+        w[:cout, :, :cin] = weight.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+        self.w_packed = w.reshape(self.cout_pad, kh * kw * self.cin_pad).half().contiguous()
+        self.bias = torch.zeros(self.cout_pad, dtype=torch.float32, device=dev)
+        if bias is not None:
+            self.bias[:cout] = bias.float()
+        if rank1_in is not None:
+            self.rank1_w = torch.zeros(self.cout_pad, dtype=torch.float32, device=dev)
+            self.rank1_w[:cout] = r1
+
+    def out_hw(self, h: int, w: int) -> Tuple[int, int]:
+        p = self.k // 2
+        return (h + 2 * p - self.k) // self.stride + 1, (w + 2 * p - self.k) // self.stride + 1
+
+
+def conv(x: torch.Tensor, pc: PackedConv, *, res: Optional[torch.Tensor] = None, rank1_x: Optional[torch.Tensor] = None,
+         want_raw: bool = False, want_relu: bool = False, want_f32: bool = False):
+    """x fp16 NHWC [B,H,W,cin_pad] -> tuple of the requested outputs (raw fp16, relu fp16, raw fp32), NHWC."""
+    assert x.dtype == torch.float16 and x.is_contiguous() and x.shape[-1] == pc.cin_pad, (x.shape, pc.cin_pad)
+    b, h, w, _ = x.shape
+    ho, wo = pc.out_hw(h, w)
+    th, tw = choose_tile(ho, wo)
+    dev = x.device
+    raw = torch.empty(b, ho, wo, pc.cout, dtype=torch.float16, device=dev) if want_raw else None
+    relu = torch.empty(b, ho, wo, pc.cout, dtype=torch.float16, device=dev) if want_relu else None
+    f32 = torch.empty(b, ho, wo, pc.cout, dtype=torch.float32, device=dev) if want_f32 else None
+    res_b = False
+    if res is not None:
+        assert res.dtype == torch.float16 and res.is_contiguous() and res.shape[1:] == (ho, wo, pc.cout)
+        res_b = res.shape[0] == 1 and b > 1
+        assert res_b or res.shape[0] == b
+    if pc.rank1_w is not None:
+        assert rank1_x is not None and rank1_x.dtype == torch.float32 and rank1_x.numel() == b * ho * wo
+    nat.conv2d(x, b, h, w, pc.cin_pad, pc.w_packed, pc.k, pc.stride, pc.cout, pc.cout_pad, pc.nt, th, tw, pc.bias,
+               res=res, res_broadcast=res_b, rank1_w=pc.rank1_w, rank1_x=rank1_x if pc.rank1_w is not None else None,
+               out_raw=raw, out_relu=relu, out_f32=f32)
+    outs = tuple(t for t in (raw, relu, f32) if t is not None)
+    return outs[0] if len(outs) == 1 else outs
+
+
+class PackedStem:
+    """7x7 stride-2 stem on (rgb [+mask]) with folded BN: weights [64, 4 k-blocks, 2 rows, 8 cols, 4 ch]."""
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor):
+        cout, cin, kh, kw = weight.shape
+        assert cout == 64 and kh == 7 and kw == 7 and cin in (3, 4)
+        w = torch.zeros(64, 8, 8, 4, dtype=torch.float32, device=weight.device)  # [cout, kh(8), kw(8), c(4)]
+        w[:, :7, :7, :cin] = weight.permute(0, 2, 3, 1)
+        self.w_packed = w.reshape(64, 256).half().contiguous()
+        self.bias = bias.float().contiguous()
+
+
+def stem(image: torch.Tensor, masks: Optional[torch.Tensor], ps: PackedStem) -> torch.Tensor:
+    """image fp32 [1,3,H,W] (masks fp32 [K,H,W] or None) -> relu(bn(conv7x7 s2)) fp16 NHWC [K,H/2,W/2,64]."""
+    _, _, h, w = image.shape
+    k = 1 if masks is None else masks.shape[0]
+    dev = image.device
+    xin = torch.empty(k, h + 6, w + 6, 4, dtype=torch.float16, device=dev)
+    nat.stem_input(image.contiguous(), None if masks is None else masks.contiguous(), xin, k, h, w)
+    out = torch.empty(k, h // 2, w // 2, 64, dtype=torch.float16, device=dev)
+    th, tw = choose_tile(h // 2, w // 2)
+    nat.stem_conv(xin, k, h, w, ps.w_packed, ps.bias, out, th, tw)
+    return out
+
+
+def maxpool(x: torch.Tensor) -> torch.Tensor:
+    b, h, w, c = x.shape
+    y = torch.empty(b, (h + 1) // 2, (w + 1) // 2, c, dtype=torch.float16, device=x.device)
+    nat.maxpool(x, y, b, h, w, c)
+    return y
+
+
+def up2_add(g: torch.Tensor, skip: torch.Tensor, want_raw=True, want_relu=True):
+    b, h, w, c = g.shape
+    assert skip.shape == (1, 2 * h, 2 * w, c)
+    raw = torch.empty(b, 2 * h, 2 * w, c, dtype=torch.float16, device=g.device) if want_raw else None
+    relu = torch.empty(b, 2 * h, 2 * w, c, dtype=torch.float16, device=g.device) if want_relu else None
+    nat.up2_add(g, skip, raw, relu, b, h, w, c)
+    return raw, relu
+
+
+def area_down(x: torch.Tensor, r: int) -> torch.Tensor:
+    b, h, w, c = x.shape
+    y = torch.empty(b, h // r, w // r, c, dtype=torch.float16, device=x.device)
+    nat.area_down(x, y, b, h, w, c, r)
+    return y
+
+
+def area_down_plane(x: torch.Tensor, r: int) -> torch.Tensor:
+    """fp32 [B,H,W] -> [B,H/r,W/r]"""
+    b, h, w = x.shape
+    y = torch.empty(b, h // r, w // r, dtype=torch.float32, device=x.device)
+    nat.area_down_plane(x.contiguous(), y, b, h, w, r)
+    return y
+
+
+def cbam_residual(x: torch.Tensor, params: dict, want_raw=True, want_relu=True):
+    """x + CBAM(x) on fp16 NHWC; params: w1,b1,w2,b2 (channel MLP), ws [2*49], bs [1] (fp32)."""
+    b, h, w, c = x.shape
+    r = params['w1'].shape[0]
+    scratch = torch.empty(3 * b * c + 2 * b * h * w, dtype=torch.float32, device=x.device)
+    raw = torch.empty_like(x) if want_raw else None
+    relu = torch.empty_like(x) if want_relu else None
+    nat.cbam(x, params['w1'], params['b1'], params['w2'], params['b2'], params['ws'], params['bs'], scratch, raw, relu,
+             b, h, w, c, r)
+    return raw, relu
+
+
+def gru(values: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
+    """values fp16 [B,H,W,3C], h fp16 [B,H,W,C] -> new h."""
+    out = torch.empty_like(h)
+    nat.gru(values, h, out, h.numel() // h.shape[-1], h.shape[-1])
+    return out
