@@ -117,6 +117,8 @@ DEVA_B200_API int deva_b200_usage(float* out, const float* use_cnt, const float*
  * eval-mode BatchNorm already folded in. */
 typedef struct deva_b200_conv_desc {
   const void* x;        /* fp16 NHWC input [batch, h, w, cin_pad] */
+  const void* x2;       /* optional second input of the same shape: the convolution sees cat[x, x2] along channels
+                         * (weights packed [cout_pad, 2, kh*kw, cin_pad]); stride 1 only */
   int32_t batch, h, w, cin_pad;
   const void* w_packed; /* fp16 [cout_pad, kh*kw*cin_pad] */
   int32_t kh, kw, stride; /* 1x1 or 3x3, stride 1 or 2, padding kh/2 (nn.Conv2d semantics) */
@@ -134,12 +136,11 @@ typedef struct deva_b200_conv_desc {
 /* nn.Conv2d + folded BatchNorm (+ residual, + ReLU) as in deva/model/resnet.py:46-114, group_modules.py:41-67,
  * modules.py:22-39; `desc` is a HOST struct. */
 DEVA_B200_API int deva_b200_conv2d(const deva_b200_conv_desc* desc, deva_stream_t stream);
-/* 7x7 stride-2 stem conv + BN + ReLU (resnet.py:120-122) on the 4-channel bordered input made by
- * deva_b200_stem_input: x fp16 [batch, h+6, w+6, 4], w_packed fp16 [64, 256], out fp16 NHWC [batch, h/2, w/2, 64]. */
-DEVA_B200_API int deva_b200_stem_conv(const void* x, int batch, int h, int w, const void* w_packed, const float* bias,
-                                      void* out_relu, int th, int tw, deva_stream_t stream);
-DEVA_B200_API int deva_b200_stem_input(const float* image, const float* masks, void* dst, int k, int h, int w,
-                                       deva_stream_t stream);
+/* im2col of the 7x7 stride-2 pad-3 stems (resnet.py:120): src fp32 planes [b, c, h, w] -> fp16 [b, h/2, w/2, k_pad],
+ * column (kh*7+kw)*c + ch, zero padded to k_pad (multiple of 64).  The stem then runs through deva_b200_conv2d as a
+ * 1x1 convolution over k_pad channels. */
+DEVA_B200_API int deva_b200_stem_im2col(const float* src, void* dst, int b, int c, int h, int w, int k_pad,
+                                        deva_stream_t stream);
 DEVA_B200_API int deva_b200_nchw_to_nhwc(const float* src, void* dst, int b, int c, int h, int w, int c_pad,
                                          deva_stream_t stream);
 DEVA_B200_API int deva_b200_nhwc_to_nchw(const void* src, float* dst, int b, int c, int h, int w, deva_stream_t stream);

@@ -68,6 +68,23 @@ def test_conv_matches_torch(b, h, w, cin, cout, k, stride):
         assert float((_nchw(f32) - ref).abs().max()) < 2e-3
 
 
+def test_conv_two_inputs():
+    """GRU transform: conv3x3 over cat[g, h] without materialising the concat."""
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(8)
+    b, h, w, c, cout = 2, 9, 12, 512, 1536
+    xa = torch.randn(b, c, h, w, device='cuda', generator=g)
+    xb = torch.randn(b, c, h, w, device='cuda', generator=g)
+    wgt = torch.randn(cout, 2 * c, 3, 3, device='cuda', generator=g) / (2 * c * 9)**0.5
+    bias = torch.randn(cout, device='cuda', generator=g)
+    pc = ops.PackedConv(wgt, bias, 1, two_inputs=True)
+    out = ops.conv(_nhwc(xa), pc, x2=_nhwc(xb), want_f32=True)
+    xin = torch.cat([_nhwc(xa).float().permute(0, 3, 1, 2), _nhwc(xb).float().permute(0, 3, 1, 2)], 1)
+    ref = F.conv2d(xin, wgt.half().float(), bias, padding=1)
+    torch.cuda.synchronize()
+    assert float((_nchw(out) - ref).abs().max()) < 2e-3
+
+
 def test_conv_rank1_term():
     ops = _ops()
     g = torch.Generator(device='cuda').manual_seed(5)
@@ -87,19 +104,20 @@ def test_conv_rank1_term():
     assert float((_nchw(out) - ref).abs().max()) < 2e-3
 
 
-@pytest.mark.parametrize('k_obj,with_mask,h,w', [(1, False, 32, 48), (3, True, 48, 80)])
-def test_stem_matches_torch(k_obj, with_mask, h, w):
+@pytest.mark.parametrize('k_obj,h,w', [(1, 32, 48), (3, 48, 80)])
+def test_stem_matches_torch(k_obj, h, w):
+    """7x7 s2 stem = shared image part (3 ch) + per-object mask part (1 ch), both through im2col + 1x1 GEMM."""
     ops = _ops()
     g = torch.Generator(device='cuda').manual_seed(11)
-    cin = 4 if with_mask else 3
     image = torch.randn(1, 3, h, w, device='cuda', generator=g)
-    masks = torch.rand(k_obj, h, w, device='cuda', generator=g) if with_mask else None
-    wgt = torch.randn(64, cin, 7, 7, device='cuda', generator=g) / (cin * 49)**0.5
+    masks = torch.rand(k_obj, 1, h, w, device='cuda', generator=g)
+    wgt = torch.randn(64, 4, 7, 7, device='cuda', generator=g) / (4 * 49)**0.5
     bias = torch.randn(64, device='cuda', generator=g) * 0.1
-    out = ops.stem(image, masks, ops.PackedStem(wgt, bias))
-    xin = image.half().float().expand(k_obj, -1, -1, -1)
-    if with_mask:
-        xin = torch.cat([xin, masks.half().float().unsqueeze(1)], 1)
+    pc_img = ops.pack_stem(wgt[:, :3], bias)
+    pc_msk = ops.pack_stem(wgt[:, 3:], None)
+    shared = ops.conv(ops.stem_columns(image, pc_img.cin_pad), pc_img, want_raw=True)
+    out = ops.conv(ops.stem_columns(masks, pc_msk.cin_pad), pc_msk, res=shared, want_relu=True)
+    xin = torch.cat([image.half().float().expand(k_obj, -1, -1, -1), masks.half().float()], 1)
     ref = F.relu(F.conv2d(xin, wgt.half().float(), bias, stride=2, padding=3))
     torch.cuda.synchronize()
     assert float((_nchw(out) - ref).abs().max()) < 1e-2

@@ -85,7 +85,7 @@ DEVA_B200_API int deva_b200_usage(float* out, const float* use_cnt, const float*
 
 DEVA_B200_API int deva_b200_conv2d(const deva_b200_conv_desc* c, deva_stream_t stream) {
   ConvDesc d;
-  d.x = c->x; d.batch = c->batch; d.h = c->h; d.w = c->w; d.cin_pad = c->cin_pad;
+  d.x = c->x; d.x2 = c->x2; d.batch = c->batch; d.h = c->h; d.w = c->w; d.cin_pad = c->cin_pad;
   d.w_packed = c->w_packed; d.kh = c->kh; d.kw = c->kw; d.stride = c->stride;
   d.cout = c->cout; d.cout_pad = c->cout_pad; d.nt = c->nt; d.th = c->th; d.tw = c->tw;
   d.bias = c->bias; d.res = c->res; d.res_broadcast = c->res_broadcast;
@@ -93,13 +93,9 @@ DEVA_B200_API int deva_b200_conv2d(const deva_b200_conv_desc* c, deva_stream_t s
   d.out_raw = c->out_raw; d.out_relu = c->out_relu; d.out_f32 = c->out_f32;
   return launch_conv(d, S(stream));
 }
-DEVA_B200_API int deva_b200_stem_conv(const void* x, int batch, int h, int w, const void* w_packed, const float* bias,
-                                      void* out_relu, int th, int tw, deva_stream_t stream) {
-  return launch_stem(x, batch, h, w, w_packed, bias, out_relu, th, tw, S(stream));
-}
-DEVA_B200_API int deva_b200_stem_input(const float* image, const float* masks, void* dst, int k, int h, int w,
-                                       deva_stream_t stream) {
-  return ew_stem_input(image, masks, H(dst), k, h, w, S(stream));
+DEVA_B200_API int deva_b200_stem_im2col(const float* src, void* dst, int b, int c, int h, int w, int k_pad,
+                                        deva_stream_t stream) {
+  return ew_stem_im2col(src, H(dst), b, c, h, w, k_pad, S(stream));
 }
 DEVA_B200_API int deva_b200_nchw_to_nhwc(const float* src, void* dst, int b, int c, int h, int w, int c_pad,
                                          deva_stream_t stream) {

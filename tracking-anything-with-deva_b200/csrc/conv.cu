@@ -288,8 +288,11 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   Params p{};
   const char* err = nullptr;
   const __half* x = reinterpret_cast<const __half*>(d.x);
-  p.taps = d.kh * d.kw;
+  const int ktaps = d.kh * d.kw;
+  const int sources = d.x2 ? 2 : 1;
+  p.taps = ktaps * sources;
   B200_REQUIRE(p.taps <= kMaxTaps, "conv: too many taps");
+  B200_REQUIRE(sources == 1 || d.stride == 1, "conv: the two-input form is stride-1 only");
   if (d.stride == 1) {
     if (make_tmap_act5(&maps.act[0], x, d.cin_pad, d.w, d.h, d.batch, (long long)d.cin_pad, (long long)d.w * d.cin_pad,
                        (long long)d.h * d.w * d.cin_pad, d.tw, d.th, &err)) {
@@ -297,10 +300,16 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
       return 3;
     }
     maps.act[1] = maps.act[2] = maps.act[3] = maps.act[0];
+    if (d.x2 && make_tmap_act5(&maps.act[1], d.x2, d.cin_pad, d.w, d.h, d.batch, (long long)d.cin_pad,
+                               (long long)d.w * d.cin_pad, (long long)d.h * d.w * d.cin_pad, d.tw, d.th, &err)) {
+      set_error("conv: %s", err ? err : "tensor map (x2)");
+      return 3;
+    }
     for (int t = 0; t < p.taps; ++t) {
-      p.tap_map[t] = 0;
-      p.tap_dy[t] = (signed char)(t / d.kw - pad);
-      p.tap_dx[t] = (signed char)(t % d.kw - pad);
+      const int kt = t % ktaps;
+      p.tap_map[t] = (signed char)(t / ktaps);
+      p.tap_dy[t] = (signed char)(kt / d.kw - pad);
+      p.tap_dx[t] = (signed char)(kt % d.kw - pad);
     }
   } else {
     // phase (py, px): rows y = 2*i + py, cols x = 2*j + px of the same NHWC buffer
@@ -347,49 +356,6 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
     configured = true;
   }
   const long long total = (long long)p.batch * p.tiles_y * p.tiles_x * p.n_tiles;
-  const int grid = (int)(total < sm_count() ? total : sm_count());
-  conv_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(maps, p);
-  B200_LAUNCH_CHECK();
-  return 0;
-}
-
-// 7x7 stride-2 pad-3 stem (resnet.py:120) on a 4-channel fp16 input with a 3-pixel zero border
-// [B, H+6, W+6, 4] (ew_stem_input).  One k-block = two filter rows x 8 columns x 4 channels = 128 contiguous
-// bytes per output pixel: tensor dims (32 = 8px*4ch, 2 rows, Wo [stride 2 px], Ho+3 [stride 2 rows], B).
-// Weights packed [64, 4 k-blocks * 64] with zeros for the 8th column / 8th row.  Output: ReLU'd NHWC fp16.
-int launch_stem(const void* x, int batch, int h, int w, const void* w_packed, const float* bias, void* out_relu,
-                int th, int tw, cudaStream_t stream) {
-  using namespace conv;
-  B200_REQUIRE(h % 2 == 0 && w % 2 == 0, "stem: odd image size %dx%d", h, w);
-  B200_REQUIRE(tw * th == 128, "stem: spatial tile %dx%d must cover 128 pixels", th, tw);
-  const int hp = h + 6, wp = w + 6, ho = h / 2, wo = w / 2;
-  Maps maps;
-  Params p{};
-  const char* err = nullptr;
-  const uint64_t dims[5] = {32, 2, (uint64_t)wo, (uint64_t)ho + 3, (uint64_t)batch};
-  const long long strides[4] = {(long long)wp * 4, 8, 2ll * wp * 4, (long long)hp * wp * 4};
-  const uint32_t box[5] = {32, 2, (uint32_t)tw, (uint32_t)th, 1};
-  if (make_tmap_f16_5d(&maps.act[0], x, dims, strides, box, &err) ||
-      make_tmap_2d(&maps.wgt, TmapType::F16, w_packed, 256, 64, 512, 64, 64, &err)) {
-    set_error("stem: %s", err ? err : "tensor map");
-    return 3;
-  }
-  maps.act[1] = maps.act[2] = maps.act[3] = maps.act[0];
-  p.taps = 4;
-  for (int t = 0; t < 4; ++t) { p.tap_map[t] = 0; p.tap_dx[t] = 0; p.tap_dy[t] = (signed char)t; }
-  p.batch = batch; p.ho = ho; p.wo = wo; p.cout = 64;
-  p.tw = tw; p.th = th;
-  p.tiles_x = ceil_div(wo, tw); p.tiles_y = ceil_div(ho, th);
-  p.nt = 64; p.n_tiles = 1; p.cblocks = 1;
-  p.pos_x = 2; p.pos_y = 3; p.pos_b = 4;
-  p.bias = bias;
-  p.out_relu = reinterpret_cast<__half*>(out_relu);
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
-  }
-  const long long total = (long long)p.batch * p.tiles_y * p.tiles_x;
   const int grid = (int)(total < sm_count() ? total : sm_count());
   conv_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(maps, p);
   B200_LAUNCH_CHECK();

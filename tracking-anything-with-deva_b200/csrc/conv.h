@@ -2,11 +2,12 @@
 #include <cuda_runtime.h>
 
 namespace b200 {
-constexpr int kMaxTaps = 16;
+constexpr int kMaxTaps = 20;
 
 // Host-side description of one convolution launch (all device pointers unless noted).
 struct ConvDesc {
   const void* x;         // fp16 NHWC [batch, h, w, cin_pad]
+  const void* x2;        // optional second input of the same shape: the conv sees cat[x, x2] along channels
   int batch, h, w, cin_pad;
   const void* w_packed;  // fp16 [cout_pad, kh*kw*cin_pad]
   int kh, kw, stride;    // 1x1 / 3x3, stride 1 / 2, padding kh/2
@@ -23,6 +24,4 @@ struct ConvDesc {
 };
 
 int launch_conv(const ConvDesc& d, cudaStream_t stream);
-int launch_stem(const void* x, int batch, int h, int w, const void* w_packed, const float* bias, void* out_relu,
-                int th, int tw, cudaStream_t stream);
 }  // namespace b200

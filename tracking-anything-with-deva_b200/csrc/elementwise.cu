@@ -40,27 +40,26 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ src, float* __res
     dst[i] = __half2float(src[(((long long)b * H + y) * W + x) * C + c]);
   }
 }
-// Stem input: image fp32 [3,H,W] (+ optional per-object mask fp32 [K,H,W]) -> fp16 [K, H+6, W+6, 4]
-// with a 3-pixel zero border (the 7x7 stride-2 padding) and channel 3 = mask (or 0).
-__global__ void stem_input_kernel(const float* __restrict__ image, const float* __restrict__ masks,
-                                  __half* __restrict__ dst, int K, int H, int W) {
-  const int Hp = H + 6, Wp = W + 6;
-  const long long total = (long long)K * Hp * Wp;
+// im2col for the 7x7 stride-2 pad-3 stems (resnet.py:120): planes fp32 [B, C, H, W] -> fp16 [B, H/2, W/2, Kp]
+// with column k = (kh*7 + kw)*C + c for k < 49*C and zeros up to Kp (a multiple of 64).  The stem then runs
+// as a 1x1 implicit GEMM over Kp "channels" on the tensor cores.
+__global__ void stem_im2col_kernel(const float* __restrict__ src, __half* __restrict__ dst, int B, int C, int H, int W,
+                                   int Kp) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * Kp;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int xp = (int)(i % Wp);
-    long long p = i / Wp;
-    const int yp = (int)(p % Hp);
-    const int k = (int)(p / Hp);
-    const int x = xp - 3, y = yp - 3;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (x >= 0 && x < W && y >= 0 && y < H) {
-      const long long o = (long long)y * W + x;
-      v[0] = image[o]; v[1] = image[(long long)H * W + o]; v[2] = image[2ll * H * W + o];
-      if (masks) v[3] = masks[(long long)k * H * W + o];
+    const int k = (int)(i % Kp);
+    long long p = i / Kp;
+    const int xo = (int)(p % Wo); p /= Wo;
+    const int yo = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float v = 0.f;
+    if (k < 49 * C) {
+      const int tap = k / C, c = k - tap * C;
+      const int y = 2 * yo + tap / 7 - 3, x = 2 * xo + tap % 7 - 3;
+      if (y >= 0 && y < H && x >= 0 && x < W) v = src[(((long long)b * C + c) * H + y) * W + x];
     }
-    __half2* d = reinterpret_cast<__half2*>(dst + i * 4);
-    d[0] = __floats2half2_rn(v[0], v[1]);
-    d[1] = __floats2half2_rn(v[2], v[3]);
+    dst[i] = __float2half_rn(v);
   }
 }
 
@@ -379,8 +378,9 @@ int ew_nhwc_to_nchw(const __half* src, float* dst, int B, int C, int H, int W, c
   B200_LAUNCH_CHECK();
   return 0;
 }
-int ew_stem_input(const float* image, const float* masks, __half* dst, int K, int H, int W, cudaStream_t s) {
-  ew::stem_input_kernel<<<grid_of((long long)K * (H + 6) * (W + 6)), 256, 0, s>>>(image, masks, dst, K, H, W);
+int ew_stem_im2col(const float* src, __half* dst, int B, int C, int H, int W, int Kp, cudaStream_t s) {
+  B200_REQUIRE(H % 2 == 0 && W % 2 == 0 && Kp % 64 == 0 && Kp >= 49 * C, "stem_im2col: bad shape");
+  ew::stem_im2col_kernel<<<grid_of((long long)B * (H / 2) * (W / 2) * Kp), 256, 0, s>>>(src, dst, B, C, H, W, Kp);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -21,7 +21,7 @@ _lib = None
 
 class ConvDesc(ctypes.Structure):
     """Mirror of ``deva_b200_conv_desc`` (include/deva_b200.h)."""
-    _fields_ = [('x', c_void_p), ('batch', c_int32), ('h', c_int32), ('w', c_int32), ('cin_pad', c_int32),
+    _fields_ = [('x', c_void_p), ('x2', c_void_p), ('batch', c_int32), ('h', c_int32), ('w', c_int32), ('cin_pad', c_int32),
                 ('w_packed', c_void_p), ('kh', c_int32), ('kw', c_int32), ('stride', c_int32),
                 ('cout', c_int32), ('cout_pad', c_int32), ('nt', c_int32), ('th', c_int32), ('tw', c_int32),
                 ('bias', c_void_p), ('res', c_void_p), ('res_broadcast', c_int32),
@@ -53,8 +53,7 @@ _SIGNATURES = {
     'deva_b200_gather_cols_f16': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     'deva_b200_usage': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'deva_b200_conv2d': (c_int, [POINTER(ConvDesc), c_void_p]),
-    'deva_b200_stem_conv': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    'deva_b200_stem_input': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'deva_b200_stem_im2col': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'deva_b200_nchw_to_nhwc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'deva_b200_nhwc_to_nchw': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'deva_b200_maxpool': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -184,9 +183,9 @@ def usage(out, use_cnt, life_cnt, n):
 
 
 # ------------------------------------------------------------------------------------------ network path
-def conv2d(x, batch, h, w, cin_pad, w_packed, kh, stride, cout, cout_pad, nt, th, tw, bias, res=None,
+def conv2d(x, batch, h, w, cin_pad, w_packed, kh, stride, cout, cout_pad, nt, th, tw, bias, x2=None, res=None,
            res_broadcast=False, rank1_w=None, rank1_x=None, out_raw=None, out_relu=None, out_f32=None):
-    d = ConvDesc(x.data_ptr(), batch, h, w, cin_pad, w_packed.data_ptr(), kh, kh, stride, cout, cout_pad, nt, th, tw,
+    d = ConvDesc(x.data_ptr(), None if x2 is None else x2.data_ptr(), batch, h, w, cin_pad, w_packed.data_ptr(), kh, kh, stride, cout, cout_pad, nt, th, tw,
                  bias.data_ptr(), None if res is None else res.data_ptr(), int(res_broadcast),
                  None if rank1_w is None else rank1_w.data_ptr(), None if rank1_x is None else rank1_x.data_ptr(),
                  None if out_raw is None else out_raw.data_ptr(), None if out_relu is None else out_relu.data_ptr(),
@@ -194,13 +193,8 @@ def conv2d(x, batch, h, w, cin_pad, w_packed, kh, stride, cout, cout_pad, nt, th
     _check(lib().deva_b200_conv2d(ctypes.byref(d), _stream()), 'conv2d')
 
 
-def stem_conv(x, batch, h, w, w_packed, bias, out_relu, th, tw):
-    _check(lib().deva_b200_stem_conv(_ptr(x), batch, h, w, _ptr(w_packed), _ptr(bias), _ptr(out_relu), th, tw,
-                                     _stream()), 'stem_conv')
-
-
-def stem_input(image, masks, dst, k, h, w):
-    _check(lib().deva_b200_stem_input(_ptr(image), _ptr(masks), _ptr(dst), k, h, w, _stream()), 'stem_input')
+def stem_im2col(src, dst, b, c, h, w, k_pad):
+    _check(lib().deva_b200_stem_im2col(_ptr(_f32(src)), _ptr(dst), b, c, h, w, k_pad, _stream()), 'stem_im2col')
 
 
 def nchw_to_nhwc(src, dst, b, c, h, w, c_pad):

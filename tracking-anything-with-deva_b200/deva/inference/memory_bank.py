@@ -99,15 +99,22 @@ class BucketBank:
 
     def append_work(self, key: torch.Tensor, shrinkage: torch.Tensor, selection: Optional[torch.Tensor],
                     values: Dict[int, torch.Tensor]) -> None:
-        """key/selection [CK, n] channel-major fp32, shrinkage [n], values {obj: [CV, n]} (kv_memory_store.py:97-116)."""
+        """key/selection: fp32 [CK, n] views (channel-major or token-major strides), shrinkage [n],
+        values {obj: [CV, n]}: fp32 channel-major, or fp16 token-major views (NHWC encoder output)
+        (kv_memory_store.py:97-116)."""
         n = key.shape[1]
         if self.hi + n > self.cap:
             self._grow(0, max(n, self.cap - self.base))
-        assert key.stride(1) == 1 and (selection is None or selection.stride() == key.stride())
-        self._write_tokens(self.hi, key, selection, key.stride(0), 1, shrinkage, n)
+        assert selection is None or selection.stride() == key.stride()
+        self._write_tokens(self.hi, key, selection, key.stride(0), key.stride(1), shrinkage, n)
         for obj, v in values.items():
-            assert v.stride(1) == 1
-            nat.append_values(v, v.stride(0), self.values[self.slot_of[obj], :, self.hi:], self.cap, self.cv, n)
+            dst = self.values[self.slot_of[obj], :, self.hi:]
+            if v.dtype == torch.float16 and v.stride(0) == 1 and v.stride(1) == self.cv:
+                nat.transpose_append(v, dst, self.cap, n, self.cv)
+            else:
+                if v.dtype != torch.float32 or v.stride(1) != 1:
+                    v = v.float().contiguous()
+                nat.append_values(v, v.stride(0), dst, self.cap, self.cv, n)
         self.hi += n
 
     def prepend_long(self, key_rows: torch.Tensor, shrinkage: torch.Tensor, values: torch.Tensor) -> None:

@@ -50,6 +50,8 @@ class MemoryManager:
         self.engaged = False
         # optional profiling hook: a list that receives one (start, end) CUDA-event pair per match_memory call
         self.read_events = None
+        # 'nhwc': match_memory returns fp16 token-major-backed views (what the native NHWC decoder consumes)
+        self.readout_layout = 'nchw'
 
     def _read_long_term_config(self, config: Dict) -> None:
         self.max_mem_frames = config['max_mid_term_frames']
@@ -78,6 +80,17 @@ class MemoryManager:
             self._scratch[name] = cur
         return cur[:need].view(*shape)
 
+    @staticmethod
+    def _ck_n(t: torch.Tensor) -> torch.Tensor:
+        """[CK, h, w] API tensor -> fp32 [CK, n] view with unit stride along one axis (no copy when possible)."""
+        ck, h, w = t.shape
+        if t.dtype == torch.float32:
+            if t.is_contiguous():
+                return t.view(ck, h * w)
+            if t.stride() == (1, w * ck, ck):  # token-major storage (NHWC engine)
+                return t.as_strided((ck, h * w), (1, ck), t.storage_offset())
+        return t.reshape(ck, h * w).float().contiguous()
+
     def _pack_query(self, qk: torch.Tensor, qe: torch.Tensor, stride_c: int, stride_q: int, q: int, tag: str):
         dev = qk.device
         q_hi = self._buf(tag + 'q_hi', (q, 2 * self.CK), torch.float16, dev)
@@ -100,16 +113,22 @@ class MemoryManager:
         h, w = query_key.shape[-2:]
         q = h * w
         dev = query_key.device
-        qk = query_key[0].reshape(self.CK, q).float().contiguous()
-        qe = selection[0].reshape(self.CK, q).float().contiguous()
+        qk = self._ck_n(query_key[0])
+        qe = self._ck_n(selection[0])
+        if qe.stride() != qk.stride():
+            qk, qe = qk.contiguous(), qe.contiguous()
         if self.read_events is not None:
             ev0 = torch.cuda.Event(enable_timing=True)
             ev0.record()
-        q_hi, q_lo, bsq = self._pack_query(qk, qe, q, 1, q, 'mm_')
+        q_hi, q_lo, bsq = self._pack_query(qk, qe, qk.stride(0), qk.stride(1), q, 'mm_')
 
         order = {obj: i for i, obj in enumerate(self._object_order())}
         k_total = len(order)
-        out = torch.empty(k_total * self.CV, q, dtype=torch.float32, device=dev)  # returned to the caller
+        nhwc = self.readout_layout == 'nhwc'
+        if nhwc:  # fp16 [K, q, CV]: per object a [CV,h,w]-shaped view of token-major storage
+            out, out_tok = None, torch.empty(k_total, q, self.CV, dtype=torch.float16, device=dev)
+        else:     # fp32 [K*CV, q]: the reference's layout
+            out, out_tok = torch.empty(k_total * self.CV, q, dtype=torch.float32, device=dev), None
         ws = self._buf('topk_ws', (nat.simtopk_workspace_bytes(q), ), torch.uint8, dev)
         idx = self._buf('topk_idx', (q, nat.LIST_PITCH), torch.int32, dev)
         wgt = self._buf('topk_w', (q, nat.LIST_PITCH), torch.float32, dev)
@@ -128,12 +147,15 @@ class MemoryManager:
                 part = objs[i:i + nat.MAX_GROUPS]
                 nat.readout(bank.values[:, :, w0:], bank.cap, bank.values.shape[0] * self.CV,
                             [bank.slot_of[o] * self.CV for o in part], [order[o] * self.CV for o in part], self.CV,
-                            aff, ldp, n_window, q, out, q)
+                            aff, ldp, n_window, q, out, q, out_tok)
         if self.read_events is not None:
             ev1 = torch.cuda.Event(enable_timing=True)
             ev1.record()
             self.read_events.append((ev0, ev1))
-        out = out.view(k_total, self.CV, h, w)
+        if nhwc:
+            out = out_tok.view(k_total, h, w, self.CV).permute(0, 3, 1, 2)
+        else:
+            out = out.view(k_total, self.CV, h, w)
         return {obj: out[i] for obj, i in order.items()}
 
     def _object_order(self) -> List[int]:
@@ -154,14 +176,20 @@ class MemoryManager:
                 self.max_work_tokens = self.max_mem_frames * self.HW
                 self.min_work_tokens = self.min_mem_frames * self.HW
         n = key.shape[-2] * key.shape[-1]
-        key = key[0].reshape(key.shape[1], n).float().contiguous()
+        key = self._ck_n(key[0])
         shr = shrinkage[0].reshape(n).float().contiguous()
         self.CK = key.shape[0]
-        value = value[0].reshape(value.shape[1], value.shape[2], n).float()
-        self.CV = value.shape[1]
+        v0 = value[0]  # [K, CV, h, w]
+        self.CV = v0.shape[1]
+        if v0.dtype == torch.float16 and v0.permute(0, 2, 3, 1).is_contiguous():
+            value = v0.as_strided((v0.shape[0], self.CV, n), (n * self.CV, 1, self.CV), v0.storage_offset())
+        else:
+            value = v0.reshape(v0.shape[0], self.CV, n).float()
         sel = None
         if selection is not None and self.use_long_term:
-            sel = selection[0].reshape(self.CK, n).float().contiguous()
+            sel = self._ck_n(selection[0])
+            if sel.stride() != key.stride():
+                key, sel = key.contiguous(), sel.contiguous()
 
         # kv_memory_store.py:67-90: known objects extend their bucket, unknown ones open ONE new bucket
         per_bank: Dict[int, Dict[int, torch.Tensor]] = {}

@@ -98,13 +98,11 @@ class ObjectManager:
                 raise NotImplementedError
             parts.append(obj_dict[obj.id])
         first = parts[0]
-        if first.is_contiguous() and all(p.is_contiguous() and p.shape == first.shape for p in parts):
-            step = first.numel() * first.element_size()
-            if all(p.data_ptr() == first.data_ptr() + i * step and
-                   p.untyped_storage().data_ptr() == first.untyped_storage().data_ptr()
-                   for i, p in enumerate(parts)):
-                return first.as_strided((len(parts), *first.shape),
-                                        (first.numel(), *first.stride()), first.storage_offset())
+        if len(parts) > 1 and all(p.shape == first.shape and p.stride() == first.stride() and p.dtype == first.dtype and
+                                  p.untyped_storage().data_ptr() == first.untyped_storage().data_ptr() for p in parts):
+            step = parts[1].storage_offset() - first.storage_offset()
+            if step > 0 and all(p.storage_offset() == first.storage_offset() + i * step for i, p in enumerate(parts)):
+                return first.as_strided((len(parts), *first.shape), (step, *first.stride()), first.storage_offset())
         return torch.stack(parts, dim=0)
 
     def make_one_hot(self, cls_mask: torch.Tensor) -> torch.Tensor:

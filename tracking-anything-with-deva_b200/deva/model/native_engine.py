@@ -1,0 +1,221 @@
+"""The DEVA propagation network on the hand-written sm_100a kernels (NHWC fp16, tcgen05 implicit GEMM).
+
+Same forward graphs as ``deva.model.engine.Engine`` (which restates the reference's network.py /
+big_modules.py / modules.py / group_modules.py / cbam.py / resnet.py with BatchNorm folded and the
+shared halves hoisted), but every layer is a ``deva_b200_conv2d`` launch with its bias / residual /
+ReLU / rank-1 input fused in the epilogue, and the glue (max-pool, bilinear x2 + skip, area pooling,
+CBAM, GRU gates, soft aggregation + x4 upsampling + softmax) runs in the helper kernels of
+csrc/elementwise.cu.  No cuDNN / cuBLAS on this path.
+
+Tensors crossing the public API keep the reference's [B, C, H, W] / [1, K, C, h, w] *shapes* but are
+permuted views of NHWC fp16 storage, so they flow through ``DEVAInferenceCore`` / ``MemoryManager``
+without conversion.
+"""
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from deva import _native as nat
+from deva.model import native_ops as ops
+from deva.model.engine import ConvSpec, LayerTable
+
+
+def _to_nhwc(t: torch.Tensor) -> torch.Tensor:
+    """API tensor [B,C,H,W] (any strides / dtype) -> contiguous fp16 [B,H,W,C]; free for our own views."""
+    x = t.permute(0, 2, 3, 1)
+    if x.dtype == torch.float16 and x.is_contiguous():
+        return x
+    if t.dtype == torch.float32 and t.is_contiguous():
+        b, c, h, w = t.shape
+        out = torch.empty(b, h, w, c, dtype=torch.float16, device=t.device)
+        nat.nchw_to_nhwc(t, out, b, c, h, w, c)
+        return out
+    return x.contiguous().half()
+
+
+def _api(t_nhwc: torch.Tensor) -> torch.Tensor:
+    return t_nhwc.permute(0, 3, 1, 2)
+
+
+class NativeEngine:
+    prefers_nhwc = True
+
+    def __init__(self, sd: Dict[str, torch.Tensor]):
+        t = LayerTable(sd)
+        self.key_dim, self.value_dim = t.key_dim, t.value_dim
+        self.device = next(iter(sd.values())).device
+        L = t.layers
+        P: Dict[str, ops.PackedConv] = {}
+        for name, spec in L.items():
+            if name.endswith('.stem') or name.endswith('.stem_img') or name.endswith('.stem_mask'):
+                P[name] = ops.pack_stem(spec.weight, spec.bias)
+            elif name.endswith('.gru'):
+                P[name] = ops.PackedConv(spec.weight, spec.bias, 1, two_inputs=True)
+            elif name.endswith('.sensory_compress'):
+                P[name] = ops.PackedConv(spec.weight, spec.bias, 1, rank1_in=spec.weight.shape[1] - 1)
+            elif name.endswith('.su.g4_conv'):
+                P[name] = ops.PackedConv(spec.weight, spec.bias, 1, rank1_in=spec.weight.shape[1] - 1)
+            else:
+                P[name] = ops.PackedConv(spec.weight, spec.bias, spec.stride)
+        self.P = P
+        self.cbam = {}
+        for p, c in t.cbam.items():
+            self.cbam[p] = dict(w1=c['w1'].contiguous(), b1=c['b1'].contiguous(), w2=c['w2'].contiguous(),
+                                b2=c['b2'].contiguous(), ws=c['ws'].reshape(-1).contiguous(), bs=c['bs'].contiguous())
+
+    # ------------------------------------------------------------------ key encoder (a10, a11)
+    def _bottleneck(self, x, q):
+        P = self.P
+        y = ops.conv(x, P[q + '.c1'], want_relu=True)
+        y = ops.conv(y, P[q + '.c2'], want_relu=True)
+        short = ops.conv(x, P[q + '.ds'], want_raw=True) if (q + '.ds') in P else x
+        return ops.conv(y, P[q + '.c3'], res=short, want_relu=True)
+
+    def encode_image(self, image: torch.Tensor):
+        """image fp32 [1,3,H,W] -> ((f16, f8, f4), key_feat) as API views of NHWC fp16 tensors."""
+        P, p = self.P, 'pixel_encoder'
+        stem = P[p + '.stem']
+        x = ops.conv(ops.stem_columns(image.float(), stem.cin_pad), stem, want_relu=True)
+        x = ops.maxpool(x)
+        feats = []
+        for stage, blocks in (('res2', 3), ('layer2', 4), ('layer3', 6)):
+            for i in range(blocks):
+                x = self._bottleneck(x, f'{p}.{stage}.{i}')
+            feats.append(x)
+        f4, f8, f16 = feats
+        f16_raw, f16_relu = ops.conv(f16, P[p + '.proj1'], want_raw=True, want_relu=True)
+        key_feat = ops.conv(f16, P[p + '.proj2'], want_raw=True)
+        f16_api = _api(f16_raw)
+        f16_api._b200_relu = f16_relu  # ReLU twin for the fusers' shared half (kept alive with the view)
+        return (f16_api, _api(f8), _api(f4)), _api(key_feat)
+
+    def transform_key(self, feat: torch.Tensor, need_sk=True, need_ek=True):
+        x = _to_nhwc(feat)
+        _, h, w, _ = x.shape
+        pc = self.P['key_proj.all']
+        y = ops.conv(x, pc, want_f32=True)  # [1,h,w,2*CK+1] fp32
+        q, ck = h * w, self.key_dim
+        key = torch.empty(q, ck, dtype=torch.float32, device=x.device)
+        sel = torch.empty(q, ck, dtype=torch.float32, device=x.device)
+        shr = torch.empty(q, dtype=torch.float32, device=x.device)
+        nat.key_tail(y, pc.cout, q, ck, key, shr, sel)
+        return (key.view(1, h, w, ck).permute(0, 3, 1, 2), shr.view(1, 1, h, w) if need_sk else None,
+                sel.view(1, h, w, ck).permute(0, 3, 1, 2) if need_ek else None)
+
+    # ------------------------------------------------------------------ shared blocks
+    def _shared_pair(self, x_api: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        raw = _to_nhwc(x_api)
+        relu = getattr(x_api, '_b200_relu', None)
+        if relu is None:
+            relu = torch.relu(raw)
+        return raw, relu
+
+    def _fuse(self, p, x_raw, x_relu, g_raw, g_relu):
+        """GroupFeatureFusionBlock (group_modules.py:133-152): returns the raw block output [K,h,w,C]."""
+        P = self.P
+        sx = ops.conv(x_relu, P[p + '.b1.c1_x'], want_raw=True)           # shared half of conv1 (+bias)
+        dx = ops.conv(x_raw, P[p + '.b1.ds_x'], want_raw=True)            # shared half of the 1x1 shortcut (+bias)
+        y = ops.conv(g_relu, P[p + '.b1.c1_g'], res=sx, want_relu=True)
+        short = ops.conv(g_raw, P[p + '.b1.ds_g'], res=dx, want_raw=True)
+        g = ops.conv(y, P[p + '.b1.c2'], res=short, want_raw=True)
+        gr_raw, gr_relu = ops.cbam_residual(g, self.cbam[p])              # g + CBAM(g)
+        y = ops.conv(gr_relu, P[p + '.b2.c1'], want_relu=True)
+        return ops.conv(y, P[p + '.b2.c2'], res=gr_raw, want_raw=True)
+
+    def _gru(self, key, g, h):
+        values = ops.conv(g, self.P[key], x2=h, want_raw=True)
+        return ops.gru(values, h)
+
+    # ------------------------------------------------------------------ value encoder (a13)
+    def _basic(self, x, q):
+        P = self.P
+        y = ops.conv(x, P[q + '.c1'], want_relu=True)
+        short = ops.conv(x, P[q + '.ds'], want_raw=True) if (q + '.ds') in P else x
+        return ops.conv(y, P[q + '.c2'], res=short, want_relu=True)
+
+    def encode_mask(self, image, ms_features, sensory, masks, deep_update=True, chunk_size=-1):
+        """image [1,3,H,W], sensory [1,K,C,h,w], masks [1,K,H,W] -> (value, sensory') as API views."""
+        P, p = self.P, 'mask_encoder'
+        k = masks.shape[1]
+        step = k if chunk_size < 1 or chunk_size >= k else chunk_size
+        img_pc, msk_pc = P[p + '.stem_img'], P[p + '.stem_mask']
+        shared = ops.conv(ops.stem_columns(image.float(), img_pc.cin_pad), img_pc, want_raw=True)
+        x_raw, x_relu = self._shared_pair(ms_features[0])
+        h_all = _to_nhwc(sensory[0])
+        planes = masks[0].float().contiguous().unsqueeze(1)  # [K,1,H,W]
+        values, hiddens = [], []
+        for i in range(0, k, step):
+            x = ops.conv(ops.stem_columns(planes[i:i + step], msk_pc.cin_pad), msk_pc, res=shared, want_relu=True)
+            x = ops.maxpool(x)  # ReLU and max-pool commute (quirk Q6)
+            for stage in ('layer1', 'layer2', 'layer3'):
+                for b in range(2):
+                    x = self._basic(x, f'{p}.{stage}.{b}')
+            g16 = self._fuse(p + '.fuser', x_raw, x_relu, x, x)
+            values.append(g16)
+            if deep_update:
+                hiddens.append(self._gru(p + '.gru', g16, h_all[i:i + step].contiguous()))
+        value = values[0] if len(values) == 1 else torch.cat(values, 0)
+        if deep_update:
+            new_h = hiddens[0] if len(hiddens) == 1 else torch.cat(hiddens, 0)
+            new_sensory = _api(new_h).unsqueeze(0)
+        else:
+            new_sensory = sensory
+        return _api(value).unsqueeze(0), new_sensory
+
+    # ------------------------------------------------------------------ decoder (a12)
+    def decode(self, ms_features, readout, sensory, last_mask, update_sensory=True, chunk_size=-1):
+        """readout/sensory [1,K,C,h,w], last_mask [1,K,H,W] -> (sensory', logits fp32 [1,K,H/4,W/4])."""
+        P, p = self.P, 'mask_decoder'
+        f16, f8, f4 = ms_features
+        k = readout.shape[1]
+        step = k if chunk_size < 1 or chunk_size >= k else chunk_size
+        x_raw, x_relu = self._shared_pair(f16)
+        skip8 = ops.conv(_to_nhwc(f8), P[p + '.skip8'], want_raw=True)
+        skip4 = ops.conv(_to_nhwc(f4), P[p + '.skip4'], want_raw=True)
+        ro_all = _to_nhwc(readout[0])
+        h_all = _to_nhwc(sensory[0])
+        hh, ww = ro_all.shape[1:3]
+        lm = last_mask[0].float().contiguous()
+        assert lm.shape[-2] == 16 * hh and lm.shape[-1] == 16 * ww
+        last = ops.area_down_plane(lm, 16)  # [K,h,w] fp32: the '+1' input channel of sensory_compress
+        logits_all, hiddens = [], []
+        for i in range(0, k, step):
+            h = h_all[i:i + step].contiguous()
+            p16_raw, p16_relu = ops.conv(h, P[p + '.sensory_compress'], rank1_x=last[i:i + step].contiguous(),
+                                         res=ro_all[i:i + step].contiguous(), want_raw=True, want_relu=True)
+            p16 = self._fuse(p + '.fuser', x_raw, x_relu, p16_raw, p16_relu)
+            g8_raw, g8_relu = ops.up2_add(p16, skip8)
+            q = p + '.up_16_8.out_conv'
+            y = ops.conv(g8_relu, P[q + '.c1'], want_relu=True)
+            short = ops.conv(g8_raw, P[q + '.ds'], want_raw=True)
+            p8 = ops.conv(y, P[q + '.c2'], res=short, want_raw=True)
+            g4_raw, g4_relu = ops.up2_add(p8, skip4)
+            q = p + '.up_8_4.out_conv'
+            y = ops.conv(g4_relu, P[q + '.c1'], want_relu=True)
+            p4_raw, p4_relu = ops.conv(y, P[q + '.c2'], res=g4_raw, want_raw=True, want_relu=True)
+            logits = ops.conv(p4_relu, P[p + '.pred'], want_f32=True)  # [k,4h,4w,1] fp32
+            logits_all.append(logits)
+            if update_sensory:
+                g = ops.conv(p16, P[p + '.su.g16_conv'], want_raw=True)
+                g = ops.conv(ops.area_down(p8, 2), P[p + '.su.g8_conv'], res=g, want_raw=True)
+                g = ops.conv(ops.area_down(p4_raw, 4), P[p + '.su.g4_conv'], res=g, want_raw=True,
+                             rank1_x=ops.area_down_plane(logits.view(-1, 4 * hh, 4 * ww), 4))
+                hiddens.append(self._gru(p + '.gru', g, h))
+        logits = logits_all[0] if len(logits_all) == 1 else torch.cat(logits_all, 0)
+        if update_sensory:
+            new_h = hiddens[0] if len(hiddens) == 1 else torch.cat(hiddens, 0)
+            new_sensory = _api(new_h).unsqueeze(0)
+        else:
+            new_sensory = sensory
+        return new_sensory, logits.view(1, k, 4 * hh, 4 * ww)
+
+    # ------------------------------------------------------------------ output tail (a14, quirk Q8)
+    def probabilities(self, logits: torch.Tensor, want_logits: bool = False):
+        """logits fp32 [1,K,h4,w4] -> prob [1,K+1,4*h4,4*w4] (and the up-sampled aggregated logits)."""
+        _, k, h4, w4 = logits.shape
+        dev = logits.device
+        agg = torch.empty(k + 1, h4, w4, dtype=torch.float32, device=dev)
+        prob = torch.empty(1, k + 1, 4 * h4, 4 * w4, dtype=torch.float32, device=dev)
+        full = torch.empty_like(prob) if want_logits else None
+        nat.output_tail(logits.contiguous(), agg, prob, full, k, h4, w4)
+        return full, prob

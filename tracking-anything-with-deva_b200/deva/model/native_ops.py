@@ -29,7 +29,7 @@ def _round_up(x, m):
 class PackedConv:
     """One convolution ready for ``deva_b200_conv2d``."""
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int,
-                 rank1_in: Optional[int] = None):
+                 rank1_in: Optional[int] = None, two_inputs: bool = False):
         """weight [Cout, Cin, k, k] fp32 (BN folded); if ``rank1_in`` is given, that input channel is split
         off as a rank-1 term (out += w[:, rank1_in] * x1) - used for the '+1' mask / logit channels."""
         cout, cin, kh, kw = weight.shape
@@ -42,6 +42,10 @@ class PackedConv:
             r1 = weight[:, rank1_in, 0, 0].float()
             weight = weight[:, keep]
             cin -= 1
+        self.two_inputs = two_inputs
+        if two_inputs:  # the layer consumes cat[x, x2]: pack [cout, source, tap, cin/2]
+            assert cin % 128 == 0 and stride == 1
+            cin //= 2
         self.cout, self.cin, self.k, self.stride = cout, cin, kh, stride
         self.cin_pad = _round_up(cin, 64)
         if cout >= 256:
@@ -51,9 +55,12 @@ class PackedConv:
         if self.nt == 0:
             self.nt = 256
         self.cout_pad = _round_up(cout, self.nt)
-        w = torch.zeros(self.cout_pad, kh * kw, self.cin_pad, dtype=torch.float32, device=dev)
-        w[:cout, :, :cin] = weight.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
-        self.w_packed = w.reshape(self.cout_pad, kh * kw * self.cin_pad).half().contiguous()
+        nsrc = 2 if two_inputs else 1
+        w = torch.zeros(self.cout_pad, nsrc, kh * kw, self.cin_pad, dtype=torch.float32, device=dev)
+        for s_ in range(nsrc):
+            part = weight[:, s_ * cin:(s_ + 1) * cin]
+            w[:cout, s_, :, :cin] = part.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+        self.w_packed = w.reshape(self.cout_pad, nsrc * kh * kw * self.cin_pad).half().contiguous()
         self.bias = torch.zeros(self.cout_pad, dtype=torch.float32, device=dev)
         if bias is not None:
             self.bias[:cout] = bias.float()
@@ -66,10 +73,14 @@ class PackedConv:
         return (h + 2 * p - self.k) // self.stride + 1, (w + 2 * p - self.k) // self.stride + 1
 
 
-def conv(x: torch.Tensor, pc: PackedConv, *, res: Optional[torch.Tensor] = None, rank1_x: Optional[torch.Tensor] = None,
-         want_raw: bool = False, want_relu: bool = False, want_f32: bool = False):
+def conv(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
+         rank1_x: Optional[torch.Tensor] = None, want_raw: bool = False, want_relu: bool = False,
+         want_f32: bool = False):
     """x fp16 NHWC [B,H,W,cin_pad] -> tuple of the requested outputs (raw fp16, relu fp16, raw fp32), NHWC."""
     assert x.dtype == torch.float16 and x.is_contiguous() and x.shape[-1] == pc.cin_pad, (x.shape, pc.cin_pad)
+    assert (x2 is not None) == pc.two_inputs
+    if x2 is not None:
+        assert x2.dtype == torch.float16 and x2.is_contiguous() and x2.shape == x.shape
     b, h, w, _ = x.shape
     ho, wo = pc.out_hw(h, w)
     th, tw = choose_tile(ho, wo)
@@ -85,33 +96,25 @@ def conv(x: torch.Tensor, pc: PackedConv, *, res: Optional[torch.Tensor] = None,
     if pc.rank1_w is not None:
         assert rank1_x is not None and rank1_x.dtype == torch.float32 and rank1_x.numel() == b * ho * wo
     nat.conv2d(x, b, h, w, pc.cin_pad, pc.w_packed, pc.k, pc.stride, pc.cout, pc.cout_pad, pc.nt, th, tw, pc.bias,
-               res=res, res_broadcast=res_b, rank1_w=pc.rank1_w, rank1_x=rank1_x if pc.rank1_w is not None else None,
+               x2=x2, res=res, res_broadcast=res_b, rank1_w=pc.rank1_w, rank1_x=rank1_x if pc.rank1_w is not None else None,
                out_raw=raw, out_relu=relu, out_f32=f32)
     outs = tuple(t for t in (raw, relu, f32) if t is not None)
     return outs[0] if len(outs) == 1 else outs
 
 
-class PackedStem:
-    """7x7 stride-2 stem on (rgb [+mask]) with folded BN: weights [64, 4 k-blocks, 2 rows, 8 cols, 4 ch]."""
-    def __init__(self, weight: torch.Tensor, bias: torch.Tensor):
-        cout, cin, kh, kw = weight.shape
-        assert cout == 64 and kh == 7 and kw == 7 and cin in (3, 4)
-        w = torch.zeros(64, 8, 8, 4, dtype=torch.float32, device=weight.device)  # [cout, kh(8), kw(8), c(4)]
-        w[:, :7, :7, :cin] = weight.permute(0, 2, 3, 1)
-        self.w_packed = w.reshape(64, 256).half().contiguous()
-        self.bias = bias.float().contiguous()
+def pack_stem(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedConv:
+    """7x7 stride-2 stem weights [64, C, 7, 7] -> a 1x1 PackedConv over the im2col columns (kh, kw, c)."""
+    cout, cin, kh, kw = weight.shape
+    assert kh == 7 and kw == 7
+    cols = weight.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin, 1, 1)
+    return PackedConv(cols, bias, 1)
 
 
-def stem(image: torch.Tensor, masks: Optional[torch.Tensor], ps: PackedStem) -> torch.Tensor:
-    """image fp32 [1,3,H,W] (masks fp32 [K,H,W] or None) -> relu(bn(conv7x7 s2)) fp16 NHWC [K,H/2,W/2,64]."""
-    _, _, h, w = image.shape
-    k = 1 if masks is None else masks.shape[0]
-    dev = image.device
-    xin = torch.empty(k, h + 6, w + 6, 4, dtype=torch.float16, device=dev)
-    nat.stem_input(image.contiguous(), None if masks is None else masks.contiguous(), xin, k, h, w)
-    out = torch.empty(k, h // 2, w // 2, 64, dtype=torch.float16, device=dev)
-    th, tw = choose_tile(h // 2, w // 2)
-    nat.stem_conv(xin, k, h, w, ps.w_packed, ps.bias, out, th, tw)
+def stem_columns(planes: torch.Tensor, k_pad: int) -> torch.Tensor:
+    """fp32 planes [B, C, H, W] -> fp16 im2col [B, H/2, W/2, k_pad] for the 7x7 stride-2 stem."""
+    b, c, h, w = planes.shape
+    out = torch.empty(b, h // 2, w // 2, k_pad, dtype=torch.float16, device=planes.device)
+    nat.stem_im2col(planes.contiguous(), out, b, c, h, w, k_pad)
     return out
 
 

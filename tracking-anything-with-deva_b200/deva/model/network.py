@@ -12,7 +12,10 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import os
+
 from deva.model.engine import Engine
+from deva.model.native_engine import NativeEngine
 from deva.model.param_spec import checkpoint_spec, synthetic_state_dict
 
 
@@ -40,6 +43,13 @@ class DEVA(nn.Module):
                 node.register_parameter(leaf, nn.Parameter(init[name].clone(), requires_grad=False))
         self._engine = None
         self._engine_key = None
+        # 'native' = hand-written sm_100a conv stack (default); 'torch' = cuDNN/ATen fp32 (debug / comparison only)
+        self.conv_backend = os.environ.get('DEVA_B200_CONV', 'native')
+        self.return_full_logits = True  # segment() also returns the up-sampled logits like the reference
+
+    @property
+    def prefers_nhwc(self) -> bool:
+        return self.conv_backend == 'native'
 
     # ------------------------------------------------------------------ weights
     def load_weights(self, src_dict: Dict[str, torch.Tensor]) -> None:
@@ -59,7 +69,8 @@ class DEVA(nn.Module):
                 raise RuntimeError('deva_b200: the network runs on a CUDA device only (call .cuda()); '
                                    'there is no CPU fallback')
             with torch.no_grad():
-                self._engine = Engine({k: v.detach() for k, v in self.state_dict().items()})
+                cls = NativeEngine if self.conv_backend == 'native' else Engine
+                self._engine = cls({k: v.detach() for k, v in self.state_dict().items()})
             self._engine_key = key
         return self._engine
 
@@ -90,6 +101,10 @@ class DEVA(nn.Module):
             raise NotImplementedError('need_aux is a training-time head; this engine is inference only')
         sensory, logits = self.engine.decode(multi_scale_features, memory_readout, sensory, last_mask,
                                              update_sensory=update_sensory, chunk_size=chunk_size)
+        if self.conv_backend == 'native' and selector is None and not independent_objects:
+            full_logits, prob = self.engine.probabilities(logits, want_logits=self.return_full_logits)
+            return sensory, full_logits, prob
+        logits = logits.float()
         prob = torch.sigmoid(logits)
         if selector is not None:
             prob = prob * selector
