@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DEVA_B200_ABI_VERSION 2
+#define DEVA_B200_ABI_VERSION 3
 #define DEVA_B200_LIST_PITCH 32 /* row pitch of top-k outputs == max supported top_k */
 #define DEVA_B200_MAX_GROUPS 256 /* objects per deva_b200_readout call */
 
@@ -119,6 +119,9 @@ typedef struct deva_b200_conv_desc {
   const void* x;        /* fp16 NHWC input [batch, h, w, cin_pad] */
   const void* x2;       /* optional second input of the same shape: the convolution sees cat[x, x2] along channels
                          * (weights packed [cout_pad, 2, kh*kw, cin_pad]); stride 1 only */
+  const void* x_lo;     /* optional fp16 low-order part of x (x_true = x + x_lo): split-precision mode
+                         * D = Xh.Wh + Xl.Wh + Xh.Wl with weights packed [cout_pad, 2 (hi, lo), kh*kw, cin_pad];
+                         * ~fp32 accuracy at 3x the MMA work.  Exclusive with x2. */
   int32_t batch, h, w, cin_pad;
   const void* w_packed; /* fp16 [cout_pad, kh*kw*cin_pad] */
   int32_t kh, kw, stride; /* 1x1 or 3x3, stride 1 or 2, padding kh/2 (nn.Conv2d semantics) */
@@ -126,26 +129,30 @@ typedef struct deva_b200_conv_desc {
   int32_t th, tw;       /* spatial tile of the implicit GEMM, th*tw == 128 */
   const float* bias;
   const void* res;      /* optional fp16 NHWC residual added before the activation (shape of the output) */
+  const void* res_lo;   /* optional low-order part of the residual */
   int32_t res_broadcast; /* 1: `res` is ONE image broadcast over the batch */
   const float* rank1_w; /* optional fp32 [cout_pad]: weight of an extra 1-channel input ... */
   const float* rank1_x; /* ... whose fp32 plane is [batch, ho*wo]  (out += rank1_w[c] * rank1_x[b, pixel]) */
   void* out_raw;        /* optional fp16 NHWC output */
   void* out_relu;       /* optional fp16 NHWC output, ReLU applied */
   float* out_f32;       /* optional fp32 NHWC output */
+  void* out_raw_lo;     /* optional fp16 remainders (value - fp16(value)) of out_raw / out_relu */
+  void* out_relu_lo;
 } deva_b200_conv_desc;
 /* nn.Conv2d + folded BatchNorm (+ residual, + ReLU) as in deva/model/resnet.py:46-114, group_modules.py:41-67,
  * modules.py:22-39; `desc` is a HOST struct. */
 DEVA_B200_API int deva_b200_conv2d(const deva_b200_conv_desc* desc, deva_stream_t stream);
 /* im2col of the 7x7 stride-2 pad-3 stems (resnet.py:120): src fp32 planes [b, c, h, w] -> fp16 [b, h/2, w/2, k_pad],
  * column (kh*7+kw)*c + ch, zero padded to k_pad (multiple of 64).  The stem then runs through deva_b200_conv2d as a
- * 1x1 convolution over k_pad channels. */
-DEVA_B200_API int deva_b200_stem_im2col(const float* src, void* dst, int b, int c, int h, int w, int k_pad,
+ * 1x1 convolution over k_pad channels.  dst_lo (optional) receives the fp16 remainders for split precision. */
+DEVA_B200_API int deva_b200_stem_im2col(const float* src, void* dst, void* dst_lo, int b, int c, int h, int w, int k_pad,
                                         deva_stream_t stream);
 DEVA_B200_API int deva_b200_nchw_to_nhwc(const float* src, void* dst, int b, int c, int h, int w, int c_pad,
                                          deva_stream_t stream);
 DEVA_B200_API int deva_b200_nhwc_to_nchw(const void* src, float* dst, int b, int c, int h, int w, deva_stream_t stream);
-/* 3x3 stride-2 max pool (resnet.py:123) */
-DEVA_B200_API int deva_b200_maxpool(const void* x, void* y, int b, int h, int w, int c, deva_stream_t stream);
+/* 3x3 stride-2 max pool (resnet.py:123); x_lo / y_lo: optional low-order parts (pooling acts on x + x_lo) */
+DEVA_B200_API int deva_b200_maxpool(const void* x, const void* x_lo, void* y, void* y_lo, int b, int h, int w, int c,
+                                    deva_stream_t stream);
 /* bilinear x2 (align_corners=False) + broadcast skip add -> raw and/or ReLU'd (modules.py:88-91) */
 DEVA_B200_API int deva_b200_up2_add(const void* g, const void* skip, void* raw, void* relu, int b, int h, int w, int c,
                                     deva_stream_t stream);

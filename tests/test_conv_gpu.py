@@ -68,6 +68,35 @@ def test_conv_matches_torch(b, h, w, cin, cout, k, stride):
         assert float((_nchw(f32) - ref).abs().max()) < 2e-3
 
 
+@pytest.mark.parametrize('stride,k', [(1, 3), (2, 3), (2, 1)])
+def test_conv_split_precision(stride, k):
+    """x = hi + lo, W = hi + lo: D = Xh.Wh + Xl.Wh + Xh.Wl reproduces the fp32 convolution to ~1e-6 relative."""
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(21 + stride + k)
+    b, h, w, cin, cout = 2, 14, 18, 128, 256
+    x = torch.randn(b, cin, h, w, device='cuda', generator=g)
+    wgt = torch.randn(cout, cin, k, k, device='cuda', generator=g) / (cin * k * k)**0.5
+    bias = torch.randn(cout, device='cuda', generator=g)
+    pc = ops.PackedConv(wgt, bias, stride, precise=True)
+    xh = _nhwc(x)
+    xl = (x.permute(0, 2, 3, 1).contiguous() - xh.float()).half()
+    ref = F.conv2d(x.double(), wgt.double(), bias.double(), stride=stride, padding=k // 2).float()
+    res = torch.randn_like(ref)
+    rh = _nhwc(res)
+    rl = (res.permute(0, 2, 3, 1).contiguous() - rh.float()).half()
+    o = ops.conv_ex(xh, pc, x_lo=xl, res=rh, res_lo=rl, want_raw=True, want_relu=True, want_f32=True, want_lo=True)
+    torch.cuda.synchronize()
+    want = ref + res
+    scale = float(want.abs().max())
+    assert float((_nchw(o.f32) - want).abs().max()) < 2e-5 * scale
+    assert float((_nchw(o.raw) + _nchw(o.raw_lo) - want).abs().max()) < 2e-5 * scale
+    assert float((_nchw(o.relu) + _nchw(o.relu_lo) - want.clamp_min(0)).abs().max()) < 2e-5 * scale
+    # pooling on pairs
+    y, y_lo = ops.maxpool(o.relu, o.relu_lo)
+    wantp = F.max_pool2d(want.clamp_min(0), 3, 2, 1)
+    assert float((_nchw(y) + _nchw(y_lo) - wantp).abs().max()) < 2e-5 * scale
+
+
 def test_conv_two_inputs():
     """GRU transform: conv3x3 over cat[g, h] without materialising the concat."""
     ops = _ops()

@@ -85,17 +85,18 @@ DEVA_B200_API int deva_b200_usage(float* out, const float* use_cnt, const float*
 
 DEVA_B200_API int deva_b200_conv2d(const deva_b200_conv_desc* c, deva_stream_t stream) {
   ConvDesc d;
-  d.x = c->x; d.x2 = c->x2; d.batch = c->batch; d.h = c->h; d.w = c->w; d.cin_pad = c->cin_pad;
+  d.x = c->x; d.x2 = c->x2; d.x_lo = c->x_lo; d.batch = c->batch; d.h = c->h; d.w = c->w; d.cin_pad = c->cin_pad;
   d.w_packed = c->w_packed; d.kh = c->kh; d.kw = c->kw; d.stride = c->stride;
   d.cout = c->cout; d.cout_pad = c->cout_pad; d.nt = c->nt; d.th = c->th; d.tw = c->tw;
-  d.bias = c->bias; d.res = c->res; d.res_broadcast = c->res_broadcast;
+  d.bias = c->bias; d.res = c->res; d.res_lo = c->res_lo; d.res_broadcast = c->res_broadcast;
   d.rank1_w = c->rank1_w; d.rank1_x = c->rank1_x;
   d.out_raw = c->out_raw; d.out_relu = c->out_relu; d.out_f32 = c->out_f32;
+  d.out_raw_lo = c->out_raw_lo; d.out_relu_lo = c->out_relu_lo;
   return launch_conv(d, S(stream));
 }
-DEVA_B200_API int deva_b200_stem_im2col(const float* src, void* dst, int b, int c, int h, int w, int k_pad,
+DEVA_B200_API int deva_b200_stem_im2col(const float* src, void* dst, void* dst_lo, int b, int c, int h, int w, int k_pad,
                                         deva_stream_t stream) {
-  return ew_stem_im2col(src, H(dst), b, c, h, w, k_pad, S(stream));
+  return ew_stem_im2col(src, H(dst), H(dst_lo), b, c, h, w, k_pad, S(stream));
 }
 DEVA_B200_API int deva_b200_nchw_to_nhwc(const float* src, void* dst, int b, int c, int h, int w, int c_pad,
                                          deva_stream_t stream) {
@@ -104,8 +105,9 @@ DEVA_B200_API int deva_b200_nchw_to_nhwc(const float* src, void* dst, int b, int
 DEVA_B200_API int deva_b200_nhwc_to_nchw(const void* src, float* dst, int b, int c, int h, int w, deva_stream_t stream) {
   return ew_nhwc_to_nchw(H(src), dst, b, c, h, w, S(stream));
 }
-DEVA_B200_API int deva_b200_maxpool(const void* x, void* y, int b, int h, int w, int c, deva_stream_t stream) {
-  return ew_maxpool(H(x), H(y), b, h, w, c, S(stream));
+DEVA_B200_API int deva_b200_maxpool(const void* x, const void* x_lo, void* y, void* y_lo, int b, int h, int w, int c,
+                                    deva_stream_t stream) {
+  return ew_maxpool(H(x), H(x_lo), H(y), H(y_lo), b, h, w, c, S(stream));
 }
 DEVA_B200_API int deva_b200_up2_add(const void* g, const void* skip, void* raw, void* relu, int b, int h, int w, int c,
                                     deva_stream_t stream) {

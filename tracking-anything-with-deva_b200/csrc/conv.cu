@@ -42,19 +42,23 @@ struct Params {
   int n_tiles, nt;
   int taps, cblocks;
   int pos_x, pos_y, pos_b;  // which TMA coordinate carries x / y / image index
-  signed char tap_map[kMaxTaps], tap_dx[kMaxTaps], tap_dy[kMaxTaps];
+  signed char tap_map[kMaxTaps], tap_w[kMaxTaps], tap_dx[kMaxTaps], tap_dy[kMaxTaps];  // per k-entry: activation
+                                                         // map, weight tap group, input offset
   const float* bias;
   const __half* res;
+  const __half* res_lo;
   long long res_batch_stride;  // elements; 0 = broadcast one image over the batch
   const float* rank1_w;
   const float* rank1_x;        // [batch, ho*wo]
   __half* out_raw;
   __half* out_relu;
   float* out_f32;
+  __half* out_raw_lo;
+  __half* out_relu_lo;
 };
 
 struct Maps {
-  CUtensorMap act[4];
+  CUtensorMap act[8];
   CUtensorMap wgt;
 };
 
@@ -64,6 +68,27 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
       : "memory");
+}
+
+// 32 fp32 values -> fp16 (and optionally the fp16 remainder value - fp16(value)), 16-byte stores
+__device__ __forceinline__ void store_split(const float (&v)[32], __half* hi, __half* lo, long long off, bool relu) {
+  if (!hi) return;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    uint4 oh, ol;
+    __half2* h2 = reinterpret_cast<__half2*>(&oh);
+    __half2* l2 = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = relu ? fmaxf(v[j + 2 * e], 0.f) : v[j + 2 * e];
+      const float b = relu ? fmaxf(v[j + 2 * e + 1], 0.f) : v[j + 2 * e + 1];
+      h2[e] = __floats2half2_rn(a, b);
+      const float2 back = __half22float2(h2[e]);
+      l2[e] = __floats2half2_rn(a - back.x, b - back.y);
+    }
+    *reinterpret_cast<uint4*>(hi + off + j) = oh;
+    if (lo) *reinterpret_cast<uint4*>(lo + off + j) = ol;
+  }
 }
 
 __device__ __forceinline__ void tile_decode(int tile, const Params& p, int& b, int& y0, int& x0, int& n0) {
@@ -98,7 +123,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
   const uint32_t stage_tx = A_BYTES + p.nt * BK * 2;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.act[i]);
+    for (int i = 0; i < 8; ++i) tma_prefetch_desc(&maps.act[i]);
     tma_prefetch_desc(&maps.wgt);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
@@ -128,7 +153,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
             mbar_expect_tx(&full[stage], stage_tx);
             c[0] = cb * BK;
             tma_load_5d(sA + stage * A_BYTES, am, &full[stage], c);
-            tma_load_2d(sB + stage * B_BYTES_MAX, &maps.wgt, &full[stage], (t * p.cblocks + cb) * BK, n0);
+            tma_load_2d(sB + stage * B_BYTES_MAX, &maps.wgt, &full[stage], (p.tap_w[t] * p.cblocks + cb) * BK, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -175,6 +200,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       const long long off = pix * p.cout + n0;
       const __half* res = p.res ? p.res + (p.res_batch_stride ? off : ((long long)y * p.wo + x) * p.cout + n0)
                                 : nullptr;
+      const __half* res_lo = p.res_lo ? p.res_lo + (res - p.res) : nullptr;
       const float r1x = (p.rank1_x && live) ? p.rank1_x[pix] : 0.f;
       const int acc = it & 1;
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
@@ -216,27 +242,21 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
                 }
               }
             }
-            if (p.out_raw) {
+            if (res_lo) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                uint4 o;
-                __half2* h2 = reinterpret_cast<__half2*>(&o);
+                const uint4 rv = *reinterpret_cast<const uint4*>(res_lo + c * 32 + j);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-                *reinterpret_cast<uint4*>(p.out_raw + off + c * 32 + j) = o;
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(h2[e]);
+                  v[j + 2 * e] += f.x;
+                  v[j + 2 * e + 1] += f.y;
+                }
               }
             }
-            if (p.out_relu) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 o;
-                __half2* h2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  h2[e] = __floats2half2_rn(fmaxf(v[j + 2 * e], 0.f), fmaxf(v[j + 2 * e + 1], 0.f));
-                *reinterpret_cast<uint4*>(p.out_relu + off + c * 32 + j) = o;
-              }
-            }
+            store_split(v, p.out_raw, p.out_raw_lo, off + c * 32, false);
+            store_split(v, p.out_relu, p.out_relu_lo, off + c * 32, true);
             if (p.out_f32) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
@@ -250,8 +270,18 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
                 float o = v[j] + p.bias[ch];
                 if (p.rank1_w) o = fmaf(p.rank1_w[ch], r1x, o);
                 if (res) o += __half2float(res[c * 32 + j]);
-                if (p.out_raw) p.out_raw[off + c * 32 + j] = __float2half_rn(o);
-                if (p.out_relu) p.out_relu[off + c * 32 + j] = __float2half_rn(fmaxf(o, 0.f));
+                if (res_lo) o += __half2float(res_lo[c * 32 + j]);
+                if (p.out_raw) {
+                  const __half hv = __float2half_rn(o);
+                  p.out_raw[off + c * 32 + j] = hv;
+                  if (p.out_raw_lo) p.out_raw_lo[off + c * 32 + j] = __float2half_rn(o - __half2float(hv));
+                }
+                if (p.out_relu) {
+                  const float ro = fmaxf(o, 0.f);
+                  const __half hv = __float2half_rn(ro);
+                  p.out_relu[off + c * 32 + j] = hv;
+                  if (p.out_relu_lo) p.out_relu_lo[off + c * 32 + j] = __float2half_rn(ro - __half2float(hv));
+                }
                 if (p.out_f32) p.out_f32[off + c * 32 + j] = o;
               }
             }
@@ -287,53 +317,61 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   Maps maps;
   Params p{};
   const char* err = nullptr;
-  const __half* x = reinterpret_cast<const __half*>(d.x);
   const int ktaps = d.kh * d.kw;
-  const int sources = d.x2 ? 2 : 1;
-  p.taps = ktaps * sources;
-  B200_REQUIRE(p.taps <= kMaxTaps, "conv: too many taps");
-  B200_REQUIRE(sources == 1 || d.stride == 1, "conv: the two-input form is stride-1 only");
-  if (d.stride == 1) {
-    if (make_tmap_act5(&maps.act[0], x, d.cin_pad, d.w, d.h, d.batch, (long long)d.cin_pad, (long long)d.w * d.cin_pad,
-                       (long long)d.h * d.w * d.cin_pad, d.tw, d.th, &err)) {
-      set_error("conv: %s", err ? err : "tensor map");
-      return 3;
-    }
-    maps.act[1] = maps.act[2] = maps.act[3] = maps.act[0];
-    if (d.x2 && make_tmap_act5(&maps.act[1], d.x2, d.cin_pad, d.w, d.h, d.batch, (long long)d.cin_pad,
-                               (long long)d.w * d.cin_pad, (long long)d.h * d.w * d.cin_pad, d.tw, d.th, &err)) {
-      set_error("conv: %s", err ? err : "tensor map (x2)");
-      return 3;
-    }
-    for (int t = 0; t < p.taps; ++t) {
-      const int kt = t % ktaps;
-      p.tap_map[t] = (signed char)(t / ktaps);
-      p.tap_dy[t] = (signed char)(kt / d.kw - pad);
-      p.tap_dx[t] = (signed char)(kt % d.kw - pad);
-    }
-  } else {
-    // phase (py, px): rows y = 2*i + py, cols x = 2*j + px of the same NHWC buffer
-    for (int py = 0; py < 2; ++py)
-      for (int px = 0; px < 2; ++px) {
+  B200_REQUIRE(!(d.x2 && d.x_lo), "conv: x2 (concat) and x_lo (split precision) are exclusive");
+  // activation sources and the (source, weight group) passes of the K loop
+  const void* srcs[2] = {d.x, d.x2 ? d.x2 : d.x_lo};
+  const int n_src = (d.x2 || d.x_lo) ? 2 : 1;
+  int pass_src[3] = {0, 0, 0}, pass_w[3] = {0, 0, 0}, n_pass = 1, w_groups = 1;
+  if (d.x2) { n_pass = 2; pass_src[1] = 1; pass_w[1] = 1; w_groups = 2; }          // cat[x, x2] . [W0 | W1]
+  if (d.x_lo) { n_pass = 3; pass_src[1] = 1; pass_w[1] = 0; pass_src[2] = 0; pass_w[2] = 1; w_groups = 2; }  // Xh.Wh + Xl.Wh + Xh.Wl
+  p.taps = ktaps * n_pass;
+  B200_REQUIRE(p.taps <= kMaxTaps, "conv: too many k-entries (%d)", p.taps);
+  const int phases = d.stride == 1 ? 1 : 4;
+  bool built[8] = {false, false, false, false, false, false, false, false};
+  for (int sidx = 0; sidx < n_src; ++sidx) {
+    const __half* xs = reinterpret_cast<const __half*>(srcs[sidx]);
+    for (int ph = 0; ph < phases; ++ph) {
+      const int py = ph / 2, px = ph % 2;
+      int rc;
+      if (d.stride == 1) {
+        rc = make_tmap_act5(&maps.act[sidx * 4], xs, d.cin_pad, d.w, d.h, d.batch, (long long)d.cin_pad,
+                            (long long)d.w * d.cin_pad, (long long)d.h * d.w * d.cin_pad, d.tw, d.th, &err);
+        built[sidx * 4] = true;
+      } else {
+        // phase (py, px): rows y = 2*i + py, cols x = 2*j + px of the same NHWC buffer
         const int hp = (d.h - py + 1) / 2, wp = (d.w - px + 1) / 2;
-        const __half* base = x + ((long long)py * d.w + px) * d.cin_pad;
-        if (hp <= 0 || wp <= 0) { maps.act[py * 2 + px] = maps.act[0]; continue; }
-        if (make_tmap_act5(&maps.act[py * 2 + px], base, d.cin_pad, wp, hp, d.batch, 2ll * d.cin_pad,
-                           2ll * d.w * d.cin_pad, (long long)d.h * d.w * d.cin_pad, d.tw, d.th, &err)) {
-          set_error("conv: %s", err ? err : "tensor map");
-          return 3;
-        }
+        if (hp <= 0 || wp <= 0) continue;
+        rc = make_tmap_act5(&maps.act[sidx * 4 + ph], xs + ((long long)py * d.w + px) * d.cin_pad, d.cin_pad, wp, hp,
+                            d.batch, 2ll * d.cin_pad, 2ll * d.w * d.cin_pad, (long long)d.h * d.w * d.cin_pad, d.tw,
+                            d.th, &err);
+        built[sidx * 4 + ph] = true;
       }
-    for (int t = 0; t < p.taps; ++t) {
-      const int oy = t / d.kw - pad, ox = t % d.kw - pad;  // input offset relative to 2*yo, 2*xo
-      const int py = ((oy % 2) + 2) % 2, px = ((ox % 2) + 2) % 2;
-      p.tap_map[t] = (signed char)(py * 2 + px);
-      p.tap_dy[t] = (signed char)((oy - py) / 2);
-      p.tap_dx[t] = (signed char)((ox - px) / 2);
+      if (rc) {
+        set_error("conv: %s", err ? err : "tensor map");
+        return 3;
+      }
     }
   }
-  if (make_tmap_2d(&maps.wgt, TmapType::F16, d.w_packed, (uint64_t)p.taps * d.cin_pad, d.cout_pad,
-                   (uint64_t)p.taps * d.cin_pad * 2, 64, d.nt, &err)) {
+  for (int i = 1; i < 8; ++i)  // unused slots still get prefetched: point them at a valid descriptor
+    if (!built[i]) maps.act[i] = maps.act[0];
+  for (int t = 0; t < p.taps; ++t) {
+    const int pass = t / ktaps, kt = t % ktaps;
+    const int oy = kt / d.kw - pad, ox = kt % d.kw - pad;  // input offset relative to stride*yo, stride*xo
+    int ph = 0, dy = oy, dx = ox;
+    if (d.stride == 2) {
+      const int py = ((oy % 2) + 2) % 2, px = ((ox % 2) + 2) % 2;
+      ph = py * 2 + px;
+      dy = (oy - py) / 2;
+      dx = (ox - px) / 2;
+    }
+    p.tap_map[t] = (signed char)(pass_src[pass] * 4 + ph);
+    p.tap_w[t] = (signed char)(pass_w[pass] * ktaps + kt);
+    p.tap_dy[t] = (signed char)dy;
+    p.tap_dx[t] = (signed char)dx;
+  }
+  if (make_tmap_2d(&maps.wgt, TmapType::F16, d.w_packed, (uint64_t)w_groups * ktaps * d.cin_pad, d.cout_pad,
+                   (uint64_t)w_groups * ktaps * d.cin_pad * 2, 64, d.nt, &err)) {
     set_error("conv: %s", err ? err : "weight tensor map");
     return 3;
   }
@@ -345,11 +383,14 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   p.pos_x = 1; p.pos_y = 2; p.pos_b = 3;
   p.bias = d.bias;
   p.res = reinterpret_cast<const __half*>(d.res);
+  p.res_lo = reinterpret_cast<const __half*>(d.res_lo);
   p.res_batch_stride = d.res_broadcast ? 0 : (long long)ho * wo * d.cout;
   p.rank1_w = d.rank1_w; p.rank1_x = d.rank1_x;
   p.out_raw = reinterpret_cast<__half*>(d.out_raw);
   p.out_relu = reinterpret_cast<__half*>(d.out_relu);
   p.out_f32 = d.out_f32;
+  p.out_raw_lo = reinterpret_cast<__half*>(d.out_raw_lo);
+  p.out_relu_lo = reinterpret_cast<__half*>(d.out_relu_lo);
   static bool configured = false;
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

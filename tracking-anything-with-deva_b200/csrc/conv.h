@@ -2,12 +2,14 @@
 #include <cuda_runtime.h>
 
 namespace b200 {
-constexpr int kMaxTaps = 20;
+constexpr int kMaxTaps = 32;
 
 // Host-side description of one convolution launch (all device pointers unless noted).
 struct ConvDesc {
   const void* x;         // fp16 NHWC [batch, h, w, cin_pad]
   const void* x2;        // optional second input of the same shape: the conv sees cat[x, x2] along channels
+  const void* x_lo;      // optional fp16 low-order part of x: split-precision mode, D = Xh.Wh + Xl.Wh + Xh.Wl
+                         // (weights packed [cout_pad, 2 (hi, lo), taps, cin_pad]); excludes x2
   int batch, h, w, cin_pad;
   const void* w_packed;  // fp16 [cout_pad, kh*kw*cin_pad]
   int kh, kw, stride;    // 1x1 / 3x3, stride 1 / 2, padding kh/2
@@ -15,12 +17,15 @@ struct ConvDesc {
   int th, tw;            // spatial tile, th*tw == 128
   const float* bias;     // [cout_pad] fp32
   const void* res;       // optional fp16 NHWC residual, same shape as the output (or one image if res_broadcast)
+  const void* res_lo;    // optional low-order part of the residual
   int res_broadcast;
   const float* rank1_w;  // optional [cout_pad]
   const float* rank1_x;  // optional [batch, ho*wo]
   void* out_raw;         // optional fp16 NHWC
   void* out_relu;        // optional fp16 NHWC, max(.,0)
   float* out_f32;        // optional fp32 NHWC
+  void* out_raw_lo;      // optional fp16 low-order parts: value - fp16(value) of out_raw / out_relu
+  void* out_relu_lo;
 };
 
 int launch_conv(const ConvDesc& d, cudaStream_t stream);

@@ -43,8 +43,8 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ src, float* __res
 // im2col for the 7x7 stride-2 pad-3 stems (resnet.py:120): planes fp32 [B, C, H, W] -> fp16 [B, H/2, W/2, Kp]
 // with column k = (kh*7 + kw)*C + c for k < 49*C and zeros up to Kp (a multiple of 64).  The stem then runs
 // as a 1x1 implicit GEMM over Kp "channels" on the tensor cores.
-__global__ void stem_im2col_kernel(const float* __restrict__ src, __half* __restrict__ dst, int B, int C, int H, int W,
-                                   int Kp) {
+__global__ void stem_im2col_kernel(const float* __restrict__ src, __half* __restrict__ dst, __half* __restrict__ dst_lo,
+                                   int B, int C, int H, int W, int Kp) {
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)B * Ho * Wo * Kp;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -59,7 +59,9 @@ __global__ void stem_im2col_kernel(const float* __restrict__ src, __half* __rest
       const int y = 2 * yo + tap / 7 - 3, x = 2 * xo + tap % 7 - 3;
       if (y >= 0 && y < H && x >= 0 && x < W) v = src[(((long long)b * C + c) * H + y) * W + x];
     }
-    dst[i] = __float2half_rn(v);
+    const __half hv = __float2half_rn(v);
+    dst[i] = hv;
+    if (dst_lo) dst_lo[i] = __float2half_rn(v - __half2float(hv));
   }
 }
 
@@ -80,7 +82,8 @@ __device__ __forceinline__ void st8(__half* p, const float (&f)[8], bool relu) {
 }
 
 // 3x3 stride-2 pad-1 max pool (resnet.py:123)
-__global__ void maxpool_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C) {
+__global__ void maxpool_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, __half* __restrict__ y,
+                               __half* __restrict__ y_lo, int B, int H, int W, int C) {
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, C8 = C / 8;
   const long long total = (long long)B * Ho * Wo * C8;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -99,12 +102,26 @@ __global__ void maxpool_kernel(const __half* __restrict__ x, __half* __restrict_
         const int xx = 2 * xo + dx;
         if (xx < 0 || xx >= W) continue;
         float f[8];
-        ld8(x + (((long long)b * H + yy) * W + xx) * C + c, f);
+        const long long o = (((long long)b * H + yy) * W + xx) * C + c;
+        ld8(x + o, f);
+        if (x_lo) {
+          float l[8];
+          ld8(x_lo + o, l);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += l[e];
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], f[e]);
       }
     }
-    st8(y + (((long long)b * Ho + yo) * Wo + xo) * C + c, m, false);
+    const long long oo = (((long long)b * Ho + yo) * Wo + xo) * C + c;
+    st8(y + oo, m, false);
+    if (y_lo) {
+      float r[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = m[e] - __half2float(__float2half_rn(m[e]));
+      st8(y_lo + oo, r, false);
+    }
   }
 }
 
@@ -378,15 +395,15 @@ int ew_nhwc_to_nchw(const __half* src, float* dst, int B, int C, int H, int W, c
   B200_LAUNCH_CHECK();
   return 0;
 }
-int ew_stem_im2col(const float* src, __half* dst, int B, int C, int H, int W, int Kp, cudaStream_t s) {
+int ew_stem_im2col(const float* src, __half* dst, __half* dst_lo, int B, int C, int H, int W, int Kp, cudaStream_t s) {
   B200_REQUIRE(H % 2 == 0 && W % 2 == 0 && Kp % 64 == 0 && Kp >= 49 * C, "stem_im2col: bad shape");
-  ew::stem_im2col_kernel<<<grid_of((long long)B * (H / 2) * (W / 2) * Kp), 256, 0, s>>>(src, dst, B, C, H, W, Kp);
+  ew::stem_im2col_kernel<<<grid_of((long long)B * (H / 2) * (W / 2) * Kp), 256, 0, s>>>(src, dst, dst_lo, B, C, H, W, Kp);
   B200_LAUNCH_CHECK();
   return 0;
 }
-int ew_maxpool(const __half* x, __half* y, int B, int H, int W, int C, cudaStream_t s) {
+int ew_maxpool(const __half* x, const __half* x_lo, __half* y, __half* y_lo, int B, int H, int W, int C, cudaStream_t s) {
   B200_REQUIRE(C % 8 == 0, "maxpool: C %% 8");
-  ew::maxpool_kernel<<<grid_of((long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8)), 256, 0, s>>>(x, y, B, H, W, C);
+  ew::maxpool_kernel<<<grid_of((long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8)), 256, 0, s>>>(x, x_lo, y, y_lo, B, H, W, C);
   B200_LAUNCH_CHECK();
   return 0;
 }

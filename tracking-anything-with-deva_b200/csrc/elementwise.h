@@ -5,8 +5,8 @@
 namespace b200 {
 int ew_nchw_to_nhwc(const float* src, __half* dst, int B, int C, int H, int W, int Cp, cudaStream_t s);
 int ew_nhwc_to_nchw(const __half* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
-int ew_stem_im2col(const float* src, __half* dst, int B, int C, int H, int W, int Kp, cudaStream_t s);
-int ew_maxpool(const __half* x, __half* y, int B, int H, int W, int C, cudaStream_t s);
+int ew_stem_im2col(const float* src, __half* dst, __half* dst_lo, int B, int C, int H, int W, int Kp, cudaStream_t s);
+int ew_maxpool(const __half* x, const __half* x_lo, __half* y, __half* y_lo, int B, int H, int W, int C, cudaStream_t s);
 int ew_up2_add(const __half* g, const __half* skip, __half* raw, __half* relu, int B, int h, int w, int C, cudaStream_t s);
 int ew_area_down(const __half* x, __half* y, int B, int H, int W, int C, int r, cudaStream_t s);
 int ew_area_down_plane(const float* x, float* y, int B, int H, int W, int r, cudaStream_t s);

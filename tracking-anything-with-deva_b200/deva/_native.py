@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libdeva_b200.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 LIST_PITCH = 32
 MAX_GROUPS = 256
 
@@ -21,12 +21,13 @@ _lib = None
 
 class ConvDesc(ctypes.Structure):
     """Mirror of ``deva_b200_conv_desc`` (include/deva_b200.h)."""
-    _fields_ = [('x', c_void_p), ('x2', c_void_p), ('batch', c_int32), ('h', c_int32), ('w', c_int32), ('cin_pad', c_int32),
+    _fields_ = [('x', c_void_p), ('x2', c_void_p), ('x_lo', c_void_p), ('batch', c_int32), ('h', c_int32), ('w', c_int32), ('cin_pad', c_int32),
                 ('w_packed', c_void_p), ('kh', c_int32), ('kw', c_int32), ('stride', c_int32),
                 ('cout', c_int32), ('cout_pad', c_int32), ('nt', c_int32), ('th', c_int32), ('tw', c_int32),
-                ('bias', c_void_p), ('res', c_void_p), ('res_broadcast', c_int32),
+                ('bias', c_void_p), ('res', c_void_p), ('res_lo', c_void_p), ('res_broadcast', c_int32),
                 ('rank1_w', c_void_p), ('rank1_x', c_void_p),
-                ('out_raw', c_void_p), ('out_relu', c_void_p), ('out_f32', c_void_p)]
+                ('out_raw', c_void_p), ('out_relu', c_void_p), ('out_f32', c_void_p),
+                ('out_raw_lo', c_void_p), ('out_relu_lo', c_void_p)]
 
 
 _SIGNATURES = {
@@ -53,10 +54,10 @@ _SIGNATURES = {
     'deva_b200_gather_cols_f16': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     'deva_b200_usage': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'deva_b200_conv2d': (c_int, [POINTER(ConvDesc), c_void_p]),
-    'deva_b200_stem_im2col': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'deva_b200_stem_im2col': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'deva_b200_nchw_to_nhwc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'deva_b200_nhwc_to_nchw': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    'deva_b200_maxpool': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'deva_b200_maxpool': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'deva_b200_up2_add': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'deva_b200_area_down': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'deva_b200_area_down_plane': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -183,18 +184,22 @@ def usage(out, use_cnt, life_cnt, n):
 
 
 # ------------------------------------------------------------------------------------------ network path
-def conv2d(x, batch, h, w, cin_pad, w_packed, kh, stride, cout, cout_pad, nt, th, tw, bias, x2=None, res=None,
-           res_broadcast=False, rank1_w=None, rank1_x=None, out_raw=None, out_relu=None, out_f32=None):
-    d = ConvDesc(x.data_ptr(), None if x2 is None else x2.data_ptr(), batch, h, w, cin_pad, w_packed.data_ptr(), kh, kh, stride, cout, cout_pad, nt, th, tw,
-                 bias.data_ptr(), None if res is None else res.data_ptr(), int(res_broadcast),
-                 None if rank1_w is None else rank1_w.data_ptr(), None if rank1_x is None else rank1_x.data_ptr(),
-                 None if out_raw is None else out_raw.data_ptr(), None if out_relu is None else out_relu.data_ptr(),
-                 None if out_f32 is None else out_f32.data_ptr())
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def conv2d(x, batch, h, w, cin_pad, w_packed, kh, stride, cout, cout_pad, nt, th, tw, bias, x2=None, x_lo=None, res=None,
+           res_lo=None, res_broadcast=False, rank1_w=None, rank1_x=None, out_raw=None, out_relu=None, out_f32=None,
+           out_raw_lo=None, out_relu_lo=None):
+    d = ConvDesc(_p(x), _p(x2), _p(x_lo), batch, h, w, cin_pad, _p(w_packed), kh, kh, stride, cout, cout_pad, nt, th, tw,
+                 _p(bias), _p(res), _p(res_lo), int(res_broadcast), _p(rank1_w), _p(rank1_x), _p(out_raw), _p(out_relu),
+                 _p(out_f32), _p(out_raw_lo), _p(out_relu_lo))
     _check(lib().deva_b200_conv2d(ctypes.byref(d), _stream()), 'conv2d')
 
 
-def stem_im2col(src, dst, b, c, h, w, k_pad):
-    _check(lib().deva_b200_stem_im2col(_ptr(_f32(src)), _ptr(dst), b, c, h, w, k_pad, _stream()), 'stem_im2col')
+def stem_im2col(src, dst, b, c, h, w, k_pad, dst_lo=None):
+    _check(lib().deva_b200_stem_im2col(_ptr(_f32(src)), _ptr(dst), _ptr(dst_lo), b, c, h, w, k_pad, _stream()),
+           'stem_im2col')
 
 
 def nchw_to_nhwc(src, dst, b, c, h, w, c_pad):
@@ -205,8 +210,8 @@ def nhwc_to_nchw(src, dst, b, c, h, w):
     _check(lib().deva_b200_nhwc_to_nchw(_ptr(src), _ptr(dst), b, c, h, w, _stream()), 'nhwc_to_nchw')
 
 
-def maxpool(x, y, b, h, w, c):
-    _check(lib().deva_b200_maxpool(_ptr(x), _ptr(y), b, h, w, c, _stream()), 'maxpool')
+def maxpool(x, y, b, h, w, c, x_lo=None, y_lo=None):
+    _check(lib().deva_b200_maxpool(_ptr(x), _ptr(x_lo), _ptr(y), _ptr(y_lo), b, h, w, c, _stream()), 'maxpool')
 
 
 def up2_add(g, skip, raw, relu, b, h, w, c):

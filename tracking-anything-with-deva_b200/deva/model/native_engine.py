@@ -47,8 +47,16 @@ class NativeEngine:
         L = t.layers
         P: Dict[str, ops.PackedConv] = {}
         for name, spec in L.items():
-            if name.endswith('.stem') or name.endswith('.stem_img') or name.endswith('.stem_mask'):
+            # The key path (pixel encoder -> key projection) and the final logit conv run in split precision
+            # (fp16 hi/lo pairs, ~fp32 accuracy): the top-k read and the sigmoid are discontinuous / steep in
+            # exactly these quantities, and together they are < 3 % of the frame's FLOPs.
+            precise = name.startswith('pixel_encoder') or name.startswith('key_proj') or name.endswith('.pred')
+            if name.endswith('.stem'):
+                P[name] = ops.pack_stem(spec.weight, spec.bias, precise=True)
+            elif name.endswith('.stem_img') or name.endswith('.stem_mask'):
                 P[name] = ops.pack_stem(spec.weight, spec.bias)
+            elif precise:
+                P[name] = ops.PackedConv(spec.weight, spec.bias, spec.stride, precise=True)
             elif name.endswith('.gru'):
                 P[name] = ops.PackedConv(spec.weight, spec.bias, 1, two_inputs=True)
             elif name.endswith('.sensory_compress'):
@@ -63,37 +71,49 @@ class NativeEngine:
             self.cbam[p] = dict(w1=c['w1'].contiguous(), b1=c['b1'].contiguous(), w2=c['w2'].contiguous(),
                                 b2=c['b2'].contiguous(), ws=c['ws'].reshape(-1).contiguous(), bs=c['bs'].contiguous())
 
-    # ------------------------------------------------------------------ key encoder (a10, a11)
+    # ------------------------------------------------------------------ key encoder (a10, a11), split precision
     def _bottleneck(self, x, q):
+        """x = (hi, lo) post-ReLU pair -> (hi, lo) pair (resnet.py:78-114 with BN folded)."""
         P = self.P
-        y = ops.conv(x, P[q + '.c1'], want_relu=True)
-        y = ops.conv(y, P[q + '.c2'], want_relu=True)
-        short = ops.conv(x, P[q + '.ds'], want_raw=True) if (q + '.ds') in P else x
-        return ops.conv(y, P[q + '.c3'], res=short, want_relu=True)
+        y = ops.conv_ex(x[0], P[q + '.c1'], x_lo=x[1], want_relu=True, want_lo=True)
+        y = ops.conv_ex(y.relu, P[q + '.c2'], x_lo=y.relu_lo, want_relu=True, want_lo=True)
+        if (q + '.ds') in P:
+            s_ = ops.conv_ex(x[0], P[q + '.ds'], x_lo=x[1], want_raw=True, want_lo=True)
+            short = (s_.raw, s_.raw_lo)
+        else:
+            short = x
+        o = ops.conv_ex(y.relu, P[q + '.c3'], x_lo=y.relu_lo, res=short[0], res_lo=short[1], want_relu=True, want_lo=True)
+        return o.relu, o.relu_lo
 
     def encode_image(self, image: torch.Tensor):
         """image fp32 [1,3,H,W] -> ((f16, f8, f4), key_feat) as API views of NHWC fp16 tensors."""
         P, p = self.P, 'pixel_encoder'
         stem = P[p + '.stem']
-        x = ops.conv(ops.stem_columns(image.float(), stem.cin_pad), stem, want_relu=True)
-        x = ops.maxpool(x)
+        cols, cols_lo = ops.stem_columns(image.float(), stem.cin_pad, with_lo=True)
+        o = ops.conv_ex(cols, stem, x_lo=cols_lo, want_relu=True, want_lo=True)
+        x = ops.maxpool(o.relu, o.relu_lo)
         feats = []
         for stage, blocks in (('res2', 3), ('layer2', 4), ('layer3', 6)):
             for i in range(blocks):
                 x = self._bottleneck(x, f'{p}.{stage}.{i}')
             feats.append(x)
         f4, f8, f16 = feats
-        f16_raw, f16_relu = ops.conv(f16, P[p + '.proj1'], want_raw=True, want_relu=True)
-        key_feat = ops.conv(f16, P[p + '.proj2'], want_raw=True)
-        f16_api = _api(f16_raw)
-        f16_api._b200_relu = f16_relu  # ReLU twin for the fusers' shared half (kept alive with the view)
-        return (f16_api, _api(f8), _api(f4)), _api(key_feat)
+        o1 = ops.conv_ex(f16[0], P[p + '.proj1'], x_lo=f16[1], want_raw=True, want_relu=True)
+        o2 = ops.conv_ex(f16[0], P[p + '.proj2'], x_lo=f16[1], want_raw=True, want_lo=True)
+        f16_api = _api(o1.raw)
+        f16_api._b200_relu = o1.relu  # ReLU twin for the fusers' shared half (kept alive with the view)
+        key_feat = _api(o2.raw)
+        key_feat._b200_lo = o2.raw_lo  # low-order part for the split-precision key projection
+        return (f16_api, _api(f8[0]), _api(f4[0])), key_feat
 
     def transform_key(self, feat: torch.Tensor, need_sk=True, need_ek=True):
         x = _to_nhwc(feat)
+        lo = getattr(feat, '_b200_lo', None)
+        if lo is None:
+            lo = torch.zeros_like(x)
         _, h, w, _ = x.shape
         pc = self.P['key_proj.all']
-        y = ops.conv(x, pc, want_f32=True)  # [1,h,w,2*CK+1] fp32
+        y = ops.conv_ex(x, pc, x_lo=lo, want_f32=True).f32  # [1,h,w,2*CK+1] fp32
         q, ck = h * w, self.key_dim
         key = torch.empty(q, ck, dtype=torch.float32, device=x.device)
         sel = torch.empty(q, ck, dtype=torch.float32, device=x.device)
@@ -192,8 +212,9 @@ class NativeEngine:
             g4_raw, g4_relu = ops.up2_add(p8, skip4)
             q = p + '.up_8_4.out_conv'
             y = ops.conv(g4_relu, P[q + '.c1'], want_relu=True)
-            p4_raw, p4_relu = ops.conv(y, P[q + '.c2'], res=g4_raw, want_raw=True, want_relu=True)
-            logits = ops.conv(p4_relu, P[p + '.pred'], want_f32=True)  # [k,4h,4w,1] fp32
+            o4 = ops.conv_ex(y, P[q + '.c2'], res=g4_raw, want_raw=True, want_relu=True, want_lo=True)
+            p4_raw = o4.raw
+            logits = ops.conv_ex(o4.relu, P[p + '.pred'], x_lo=o4.relu_lo, want_f32=True).f32  # [k,4h,4w,1] fp32
             logits_all.append(logits)
             if update_sensory:
                 g = ops.conv(p16, P[p + '.su.g16_conv'], want_raw=True)

@@ -29,7 +29,7 @@ def _round_up(x, m):
 class PackedConv:
     """One convolution ready for ``deva_b200_conv2d``."""
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int,
-                 rank1_in: Optional[int] = None, two_inputs: bool = False):
+                 rank1_in: Optional[int] = None, two_inputs: bool = False, precise: bool = False):
         """weight [Cout, Cin, k, k] fp32 (BN folded); if ``rank1_in`` is given, that input channel is split
         off as a rank-1 term (out += w[:, rank1_in] * x1) - used for the '+1' mask / logit channels."""
         cout, cin, kh, kw = weight.shape
@@ -43,6 +43,8 @@ class PackedConv:
             weight = weight[:, keep]
             cin -= 1
         self.two_inputs = two_inputs
+        self.precise = precise  # split precision: weights stored as fp16 (hi, lo), inputs arrive as (hi, lo)
+        assert not (two_inputs and precise)
         if two_inputs:  # the layer consumes cat[x, x2]: pack [cout, source, tap, cin/2]
             assert cin % 128 == 0 and stride == 1
             cin //= 2
@@ -60,6 +62,11 @@ class PackedConv:
         for s_ in range(nsrc):
             part = weight[:, s_ * cin:(s_ + 1) * cin]
             w[:cout, s_, :, :cin] = part.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+        if precise:
+            hi = w.half()
+            lo = (w - hi.float()).half()
+            w = torch.cat([hi.float(), lo.float()], 1)
+            nsrc = 2
         self.w_packed = w.reshape(self.cout_pad, nsrc * kh * kw * self.cin_pad).half().contiguous()
         self.bias = torch.zeros(self.cout_pad, dtype=torch.float32, device=dev)
         if bias is not None:
@@ -73,56 +80,88 @@ class PackedConv:
         return (h + 2 * p - self.k) // self.stride + 1, (w + 2 * p - self.k) // self.stride + 1
 
 
-def conv(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
-         rank1_x: Optional[torch.Tensor] = None, want_raw: bool = False, want_relu: bool = False,
-         want_f32: bool = False):
-    """x fp16 NHWC [B,H,W,cin_pad] -> tuple of the requested outputs (raw fp16, relu fp16, raw fp32), NHWC."""
+class ConvOut:
+    __slots__ = ('raw', 'raw_lo', 'relu', 'relu_lo', 'f32')
+
+    def __init__(self):
+        self.raw = self.raw_lo = self.relu = self.relu_lo = self.f32 = None
+
+
+def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = None, x_lo: Optional[torch.Tensor] = None,
+            res: Optional[torch.Tensor] = None, res_lo: Optional[torch.Tensor] = None,
+            rank1_x: Optional[torch.Tensor] = None, want_raw: bool = False, want_relu: bool = False,
+            want_f32: bool = False, want_lo: bool = False) -> ConvOut:
+    """x fp16 NHWC [B,H,W,cin_pad] (+ x2: implicit channel concat, or + x_lo: split precision) -> ConvOut."""
     assert x.dtype == torch.float16 and x.is_contiguous() and x.shape[-1] == pc.cin_pad, (x.shape, pc.cin_pad)
-    assert (x2 is not None) == pc.two_inputs
-    if x2 is not None:
-        assert x2.dtype == torch.float16 and x2.is_contiguous() and x2.shape == x.shape
+    assert (x2 is not None) == pc.two_inputs and (x_lo is not None) == pc.precise
+    for other in (x2, x_lo):
+        if other is not None:
+            assert other.dtype == torch.float16 and other.is_contiguous() and other.shape == x.shape
     b, h, w, _ = x.shape
     ho, wo = pc.out_hw(h, w)
     th, tw = choose_tile(ho, wo)
     dev = x.device
-    raw = torch.empty(b, ho, wo, pc.cout, dtype=torch.float16, device=dev) if want_raw else None
-    relu = torch.empty(b, ho, wo, pc.cout, dtype=torch.float16, device=dev) if want_relu else None
-    f32 = torch.empty(b, ho, wo, pc.cout, dtype=torch.float32, device=dev) if want_f32 else None
+
+    def new(dtype=torch.float16):
+        return torch.empty(b, ho, wo, pc.cout, dtype=dtype, device=dev)
+
+    o = ConvOut()
+    if want_raw:
+        o.raw = new()
+        o.raw_lo = new() if want_lo else None
+    if want_relu:
+        o.relu = new()
+        o.relu_lo = new() if want_lo else None
+    if want_f32:
+        o.f32 = new(torch.float32)
     res_b = False
     if res is not None:
         assert res.dtype == torch.float16 and res.is_contiguous() and res.shape[1:] == (ho, wo, pc.cout)
         res_b = res.shape[0] == 1 and b > 1
         assert res_b or res.shape[0] == b
+        assert res_lo is None or (res_lo.shape == res.shape and res_lo.is_contiguous())
     if pc.rank1_w is not None:
         assert rank1_x is not None and rank1_x.dtype == torch.float32 and rank1_x.numel() == b * ho * wo
     nat.conv2d(x, b, h, w, pc.cin_pad, pc.w_packed, pc.k, pc.stride, pc.cout, pc.cout_pad, pc.nt, th, tw, pc.bias,
-               x2=x2, res=res, res_broadcast=res_b, rank1_w=pc.rank1_w, rank1_x=rank1_x if pc.rank1_w is not None else None,
-               out_raw=raw, out_relu=relu, out_f32=f32)
-    outs = tuple(t for t in (raw, relu, f32) if t is not None)
+               x2=x2, x_lo=x_lo, res=res, res_lo=res_lo, res_broadcast=res_b, rank1_w=pc.rank1_w,
+               rank1_x=rank1_x if pc.rank1_w is not None else None, out_raw=o.raw, out_relu=o.relu, out_f32=o.f32,
+               out_raw_lo=o.raw_lo, out_relu_lo=o.relu_lo)
+    return o
+
+
+def conv(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
+         rank1_x: Optional[torch.Tensor] = None, want_raw: bool = False, want_relu: bool = False,
+         want_f32: bool = False):
+    """Plain-precision convenience form: returns the requested outputs (raw fp16, relu fp16, raw fp32) as a tuple
+    (or the single tensor)."""
+    o = conv_ex(x, pc, x2=x2, res=res, rank1_x=rank1_x, want_raw=want_raw, want_relu=want_relu, want_f32=want_f32)
+    outs = tuple(t for t in (o.raw, o.relu, o.f32) if t is not None)
     return outs[0] if len(outs) == 1 else outs
 
 
-def pack_stem(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedConv:
+def pack_stem(weight: torch.Tensor, bias: Optional[torch.Tensor], precise: bool = False) -> PackedConv:
     """7x7 stride-2 stem weights [64, C, 7, 7] -> a 1x1 PackedConv over the im2col columns (kh, kw, c)."""
     cout, cin, kh, kw = weight.shape
     assert kh == 7 and kw == 7
     cols = weight.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin, 1, 1)
-    return PackedConv(cols, bias, 1)
+    return PackedConv(cols, bias, 1, precise=precise)
 
 
-def stem_columns(planes: torch.Tensor, k_pad: int) -> torch.Tensor:
-    """fp32 planes [B, C, H, W] -> fp16 im2col [B, H/2, W/2, k_pad] for the 7x7 stride-2 stem."""
+def stem_columns(planes: torch.Tensor, k_pad: int, with_lo: bool = False):
+    """fp32 planes [B, C, H, W] -> fp16 im2col [B, H/2, W/2, k_pad] (and its fp16 remainder) for the 7x7 stride-2 stem."""
     b, c, h, w = planes.shape
     out = torch.empty(b, h // 2, w // 2, k_pad, dtype=torch.float16, device=planes.device)
-    nat.stem_im2col(planes.contiguous(), out, b, c, h, w, k_pad)
-    return out
+    lo = torch.empty_like(out) if with_lo else None
+    nat.stem_im2col(planes.contiguous(), out, b, c, h, w, k_pad, dst_lo=lo)
+    return (out, lo) if with_lo else out
 
 
-def maxpool(x: torch.Tensor) -> torch.Tensor:
+def maxpool(x: torch.Tensor, x_lo: Optional[torch.Tensor] = None):
     b, h, w, c = x.shape
     y = torch.empty(b, (h + 1) // 2, (w + 1) // 2, c, dtype=torch.float16, device=x.device)
-    nat.maxpool(x, y, b, h, w, c)
-    return y
+    y_lo = torch.empty_like(y) if x_lo is not None else None
+    nat.maxpool(x, y, b, h, w, c, x_lo=x_lo, y_lo=y_lo)
+    return (y, y_lo) if x_lo is not None else y
 
 
 def up2_add(g: torch.Tensor, skip: torch.Tensor, want_raw=True, want_relu=True):
