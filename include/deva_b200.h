@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DEVA_B200_ABI_VERSION 3
+#define DEVA_B200_ABI_VERSION 4
 #define DEVA_B200_LIST_PITCH 32 /* row pitch of top-k outputs == max supported top_k */
 #define DEVA_B200_MAX_GROUPS 256 /* objects per deva_b200_readout call */
 
@@ -138,6 +138,9 @@ typedef struct deva_b200_conv_desc {
   float* out_f32;       /* optional fp32 NHWC output */
   void* out_raw_lo;     /* optional fp16 remainders (value - fp16(value)) of out_raw / out_relu */
   void* out_relu_lo;
+  const float* head_w;  /* optional fused 1x1 head on the ReLU'd fp32 result (needs cout_pad == nt): fp32 [head_n, cout] */
+  float* head_out;      /* fp32 [batch*ho*wo, head_n]: head_out[p, t] = sum_c relu(out[p, c]) * head_w[t, c] */
+  int32_t head_n;       /* <= 9.  Folds MaskDecoder.pred (big_modules.py:189-190) into the last decoder conv. */
 } deva_b200_conv_desc;
 /* nn.Conv2d + folded BatchNorm (+ residual, + ReLU) as in deva/model/resnet.py:46-114, group_modules.py:41-67,
  * modules.py:22-39; `desc` is a HOST struct. */
@@ -159,7 +162,7 @@ DEVA_B200_API int deva_b200_up2_add(const void* g, const void* skip, void* raw, 
 /* F.interpolate(mode='area') by an integer ratio r (group_modules.py:33-38), fp16 NHWC and fp32 planes */
 DEVA_B200_API int deva_b200_area_down(const void* x, void* y, int b, int h, int w, int c, int r, deva_stream_t stream);
 DEVA_B200_API int deva_b200_area_down_plane(const float* x, float* y, int b, int h, int w, int r, deva_stream_t stream);
-/* x + CBAM(x) (cbam.py:21-77 inside group_modules.py:146-150); scratch: fp32 [3*b*c + 2*b*h*w] */
+/* x + CBAM(x) (cbam.py:21-77 inside group_modules.py:146-150); scratch: fp32 [33*b*c + 2*b*h*w] */
 DEVA_B200_API int deva_b200_cbam(const void* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                  const float* ws, const float* bs, float* scratch, void* raw, void* relu, int b, int h,
                                  int w, int c, int r, deva_stream_t stream);
@@ -173,6 +176,10 @@ DEVA_B200_API int deva_b200_key_tail(const float* y, int ld, int q, int ck, floa
  * prob fp32 [(k+1),4h,4w] (and optionally the up-sampled logits); agg: fp32 scratch [(k+1),h,w] */
 DEVA_B200_API int deva_b200_output_tail(const float* logits, float* agg, float* prob, float* logits_out, int k, int h,
                                         int w, deva_stream_t stream);
+/* logits[b,y,x] = bias + sum_{dy,dx} z[b, y+dy, x+dx, (dy+1)*3+(dx+1)]: the 3x3 gather completing the fused head
+ * (z fp32 [b,h,w,9] from deva_b200_conv2d's head_out) == nn.Conv2d(256, 1, 3, padding=1) on relu(p4) */
+DEVA_B200_API int deva_b200_head_gather3x3(const float* z, float* out, float bias, int b, int h, int w,
+                                           deva_stream_t stream);
 /* fp16 token-major values [n, c] -> bank rows dst[c, j] (ld_dst): append from the NHWC value encoder */
 DEVA_B200_API int deva_b200_transpose_append(const void* src, void* dst, int64_t ld_dst, int n, int c,
                                              deva_stream_t stream);

@@ -97,6 +97,30 @@ def test_conv_split_precision(stride, k):
     assert float((_nchw(y) + _nchw(y_lo) - wantp).abs().max()) < 2e-5 * scale
 
 
+def test_conv_fused_head_equals_3x3_conv():
+    """c2 + residual, then pred(relu(.)) via the fused 9-tap head + gather == two separate convolutions."""
+    ops = _ops()
+    from deva import _native as nat
+    g = torch.Generator(device='cuda').manual_seed(31)
+    b, h, w, c = 2, 13, 22, 256
+    x = torch.randn(b, c, h, w, device='cuda', generator=g)
+    res = torch.randn(b, c, h, w, device='cuda', generator=g)
+    wgt = torch.randn(c, c, 3, 3, device='cuda', generator=g) / (c * 9)**0.5
+    bias = torch.randn(c, device='cuda', generator=g)
+    pw = torch.randn(1, c, 3, 3, device='cuda', generator=g) / (c * 9)**0.5 * 3
+    pb = 0.3
+    pc = ops.PackedConv(wgt, bias, 1)
+    head_w = pw[0].permute(1, 2, 0).reshape(9, c).contiguous()
+    o = ops.conv_ex(_nhwc(x), pc, res=_nhwc(res), want_raw=True, head_w=head_w)
+    logits = torch.empty(b, h, w, 1, device='cuda')
+    nat.head_gather3x3(o.head, logits, pb, b, h, w)
+    p4 = F.conv2d(_nhwc(x).float().permute(0, 3, 1, 2), wgt.half().float(), bias, padding=1) + _nhwc(res).float().permute(0, 3, 1, 2)
+    ref = F.conv2d(F.relu(p4), pw, torch.tensor([pb], device='cuda'), padding=1)
+    torch.cuda.synchronize()
+    assert float((_nchw(o.raw) - p4).abs().max()) < 1e-2
+    assert float((logits.permute(0, 3, 1, 2) - ref).abs().max()) < 2e-3
+
+
 def test_conv_two_inputs():
     """GRU transform: conv3x3 over cat[g, h] without materialising the concat."""
     ops = _ops()

@@ -92,6 +92,7 @@ DEVA_B200_API int deva_b200_conv2d(const deva_b200_conv_desc* c, deva_stream_t s
   d.rank1_w = c->rank1_w; d.rank1_x = c->rank1_x;
   d.out_raw = c->out_raw; d.out_relu = c->out_relu; d.out_f32 = c->out_f32;
   d.out_raw_lo = c->out_raw_lo; d.out_relu_lo = c->out_relu_lo;
+  d.head_w = c->head_w; d.head_out = c->head_out; d.head_n = c->head_n;
   return launch_conv(d, S(stream));
 }
 DEVA_B200_API int deva_b200_stem_im2col(const float* src, void* dst, void* dst_lo, int b, int c, int h, int w, int k_pad,
@@ -135,6 +136,10 @@ DEVA_B200_API int deva_b200_key_tail(const float* y, int ld, int q, int ck, floa
 DEVA_B200_API int deva_b200_output_tail(const float* logits, float* agg, float* prob, float* logits_out, int k, int h,
                                         int w, deva_stream_t stream) {
   return ew_output_tail(logits, agg, prob, logits_out, k, h, w, S(stream));
+}
+DEVA_B200_API int deva_b200_head_gather3x3(const float* z, float* out, float bias, int b, int h, int w,
+                                           deva_stream_t stream) {
+  return ew_head_gather3x3(z, out, bias, b, h, w, S(stream));
 }
 DEVA_B200_API int deva_b200_transpose_append(const void* src, void* dst, int64_t ld_dst, int n, int c,
                                              deva_stream_t stream) {

@@ -34,7 +34,8 @@ constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES_MAX = 256 * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int HEAD_BYTES = kMaxHead * 256 * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + HEAD_BYTES;
 
 struct Params {
   int batch, ho, wo, cout;
@@ -55,6 +56,9 @@ struct Params {
   float* out_f32;
   __half* out_raw_lo;
   __half* out_relu_lo;
+  const float* head_w;
+  float* head_out;
+  int head_n;
 };
 
 struct Maps {
@@ -115,6 +119,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
   uint64_t* acc_full = bars + 2 * STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_head = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [kMaxHead][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -190,6 +195,13 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
     const int row = quad * 32 + lane;  // pixel within the tile
     const int ty = row / p.tw, tx = row - ty * p.tw;
     const bool vec_ok = (p.cout % 8) == 0;
+    if (p.head_w) {  // stage the head weights once per CTA (epilogue warps only)
+      for (int i = threadIdx.x - 64; i < kMaxHead * 256; i += 128) {
+        const int t = i / 256, ch = i - t * 256;
+        s_head[i] = (t < p.head_n && ch < p.cout) ? p.head_w[t * p.cout + ch] : 0.f;
+      }
+      named_bar_sync(1, 128);
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int b, y0, x0, n0;
@@ -203,6 +215,9 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       const __half* res_lo = p.res_lo ? p.res_lo + (res - p.res) : nullptr;
       const float r1x = (p.rank1_x && live) ? p.rank1_x[pix] : 0.f;
       const int acc = it & 1;
+      float hacc[kMaxHead];
+#pragma unroll
+      for (int t = 0; t < kMaxHead; ++t) hacc[t] = 0.f;
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -257,6 +272,20 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
             }
             store_split(v, p.out_raw, p.out_raw_lo, off + c * 32, false);
             store_split(v, p.out_relu, p.out_relu_lo, off + c * 32, true);
+            if (p.head_w) {
+#pragma unroll
+              for (int t = 0; t < kMaxHead; ++t) {
+                const float4* w4 = reinterpret_cast<const float4*>(s_head + t * 256 + c * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 wv = w4[j];
+                  hacc[t] = fmaf(fmaxf(v[4 * j], 0.f), wv.x, hacc[t]);
+                  hacc[t] = fmaf(fmaxf(v[4 * j + 1], 0.f), wv.y, hacc[t]);
+                  hacc[t] = fmaf(fmaxf(v[4 * j + 2], 0.f), wv.z, hacc[t]);
+                  hacc[t] = fmaf(fmaxf(v[4 * j + 3], 0.f), wv.w, hacc[t]);
+                }
+              }
+            }
             if (p.out_f32) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
@@ -291,6 +320,9 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (p.head_w && live) {
+        for (int t = 0; t < p.head_n; ++t) p.head_out[pix * p.head_n + t] = hacc[t];
+      }
     }
   }
 
@@ -391,6 +423,11 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   p.out_f32 = d.out_f32;
   p.out_raw_lo = reinterpret_cast<__half*>(d.out_raw_lo);
   p.out_relu_lo = reinterpret_cast<__half*>(d.out_relu_lo);
+  if (d.head_w) {
+    B200_REQUIRE(d.cout_pad == d.nt && d.cout % 32 == 0 && d.cout <= 256 && d.head_n >= 1 && d.head_n <= kMaxHead && d.head_out,
+                 "conv: fused head needs the whole Cout (%d) in one channel tile and head_n <= %d", d.cout, kMaxHead);
+    p.head_w = d.head_w; p.head_out = d.head_out; p.head_n = d.head_n;
+  }
   static bool configured = false;
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -3,6 +3,7 @@
 
 namespace b200 {
 constexpr int kMaxTaps = 32;
+constexpr int kMaxHead = 9;
 
 // Host-side description of one convolution launch (all device pointers unless noted).
 struct ConvDesc {
@@ -26,6 +27,12 @@ struct ConvDesc {
   float* out_f32;        // optional fp32 NHWC
   void* out_raw_lo;      // optional fp16 low-order parts: value - fp16(value) of out_raw / out_relu
   void* out_relu_lo;
+  // optional fused 1x1 'head' on the ReLU'd fp32 result (needs cout_pad == nt): head_out[pixel, t] =
+  // sum_c relu(out[pixel, c]) * head_w[t, c], t < head_n <= kMaxHead.  Used to fold the 3x3 logit conv
+  // (MaskDecoder.pred) into the last decoder conv: the 9 taps are gathered afterwards by ew_head_gather3x3.
+  const float* head_w;   // [head_n, cout] fp32
+  float* head_out;       // [batch*ho*wo, head_n] fp32
+  int head_n;
 };
 
 int launch_conv(const ConvDesc& d, cudaStream_t stream);

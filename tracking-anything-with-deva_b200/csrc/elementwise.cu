@@ -43,25 +43,27 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ src, float* __res
 // im2col for the 7x7 stride-2 pad-3 stems (resnet.py:120): planes fp32 [B, C, H, W] -> fp16 [B, H/2, W/2, Kp]
 // with column k = (kh*7 + kw)*C + c for k < 49*C and zeros up to Kp (a multiple of 64).  The stem then runs
 // as a 1x1 implicit GEMM over Kp "channels" on the tensor cores.
-__global__ void stem_im2col_kernel(const float* __restrict__ src, __half* __restrict__ dst, __half* __restrict__ dst_lo,
-                                   int B, int C, int H, int W, int Kp) {
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ src, __half* __restrict__ dst, __half* __restrict__ dst_lo,
+                   int B, int C, int H, int W, int Kp) {
+  // blockIdx.y = (image, output row); threads sweep (output column, k) with k fastest -> coalesced stores
   const int Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)B * Ho * Wo * Kp;
-  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int k = (int)(i % Kp);
-    long long p = i / Kp;
-    const int xo = (int)(p % Wo); p /= Wo;
-    const int yo = (int)(p % Ho);
-    const int b = (int)(p / Ho);
+  const int b = blockIdx.y / Ho, yo = blockIdx.y - b * Ho;
+  const int row_elems = Wo * Kp;
+  const float* img = src + (long long)b * C * H * W;
+  const long long out_base = ((long long)b * Ho + yo) * (long long)row_elems;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < row_elems; i += gridDim.x * 256) {
+    const int xo = i / Kp, k = i - xo * Kp;
     float v = 0.f;
     if (k < 49 * C) {
       const int tap = k / C, c = k - tap * C;
-      const int y = 2 * yo + tap / 7 - 3, x = 2 * xo + tap % 7 - 3;
-      if (y >= 0 && y < H && x >= 0 && x < W) v = src[(((long long)b * C + c) * H + y) * W + x];
+      const int ky = tap / 7, kx = tap - ky * 7;
+      const int y = 2 * yo + ky - 3, x = 2 * xo + kx - 3;
+      if (y >= 0 && y < H && x >= 0 && x < W) v = img[((long long)c * H + y) * W + x];
     }
     const __half hv = __float2half_rn(v);
-    dst[i] = hv;
-    if (dst_lo) dst_lo[i] = __float2half_rn(v - __half2float(hv));
+    dst[out_base + i] = hv;
+    if (dst_lo) dst_lo[out_base + i] = __float2half_rn(v - __half2float(hv));
   }
 }
 
@@ -127,34 +129,37 @@ __global__ void maxpool_kernel(const __half* __restrict__ x, const __half* __res
 
 // out = bilinear_x2(g) + skip (skip is one image broadcast over the batch); writes raw and/or relu
 // (MaskUpsampleBlock: upsample_groups + distributor 'add', modules.py:88-91)
-__global__ void up2_add_kernel(const __half* __restrict__ g, const __half* __restrict__ skip, __half* __restrict__ raw,
-                               __half* __restrict__ relu, int B, int h, int w, int C) {
+__global__ void __launch_bounds__(256)
+up2_add_kernel(const __half* __restrict__ g, const __half* __restrict__ skip, __half* __restrict__ raw,
+               __half* __restrict__ relu, int B, int h, int w, int C) {
+  // blockIdx.y = (image, output row): the two source rows and their weights are uniform per block
   const int H = 2 * h, W = 2 * w, C8 = C / 8;
-  const long long total = (long long)B * H * W * C8;
-  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int c = (int)(i % C8) * 8;
-    long long p = i / C8;
-    const int X = (int)(p % W); p /= W;
-    const int Y = (int)(p % H);
-    const int b = (int)(p / H);
-    // align_corners=False: src = (dst + 0.5)/2 - 0.5, clamped at 0
-    const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.f);
-    const int y0 = (int)sy, x0 = (int)sx;
-    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-    const float wy = sy - y0, wx = sx - x0;
-    float a[8], bq[8], cq[8], d[8], o[8], s[8];
-    const __half* gb = g + (long long)b * h * w * C + c;
-    ld8(gb + ((long long)y0 * w + x0) * C, a);
-    ld8(gb + ((long long)y0 * w + x1) * C, bq);
-    ld8(gb + ((long long)y1 * w + x0) * C, cq);
-    ld8(gb + ((long long)y1 * w + x1) * C, d);
-    ld8(skip + ((long long)Y * W + X) * C + c, s);
+  const int b = blockIdx.y / H, Y = blockIdx.y - b * H;
+  const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.f);  // align_corners=False: src = (dst + 0.5)/2 - 0.5, clamped
+  const int y0 = (int)sy, y1 = min(y0 + 1, h - 1);
+  const float wy = sy - y0;
+  const __half* r0 = g + ((long long)b * h + y0) * w * C;
+  const __half* r1 = g + ((long long)b * h + y1) * w * C;
+  const __half* sk = skip + (long long)Y * W * C;
+  const long long obase = ((long long)b * H + Y) * W * C;
+  const int row_vecs = W * C8;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < row_vecs; i += gridDim.x * 256) {
+    const int X = i / C8, c = (i - X * C8) * 8;
+    const float sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.f);
+    const int x0 = (int)sx, x1 = min(x0 + 1, w - 1);
+    const float wx = sx - x0;
+    float a[8], bq[8], cq[8], d[8], o[8], s_[8];
+    ld8(r0 + x0 * C + c, a);
+    ld8(r0 + x1 * C + c, bq);
+    ld8(r1 + x0 * C + c, cq);
+    ld8(r1 + x1 * C + c, d);
+    ld8(sk + X * C + c, s_);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float top = a[e] + (bq[e] - a[e]) * wx, bot = cq[e] + (d[e] - cq[e]) * wx;
-      o[e] = top + (bot - top) * wy + s[e];
+      o[e] = top + (bot - top) * wy + s_[e];
     }
-    const long long off = (((long long)b * H + Y) * W + X) * C + c;
+    const long long off = obase + X * C + c;
     if (raw) st8(raw + off, o, false);
     if (relu) st8(relu + off, o, true);
   }
@@ -202,33 +207,51 @@ __global__ void area_down_plane_kernel(const float* __restrict__ x, float* __res
 }
 
 // ---------------------------------------------------------------- CBAM (cbam.py:21-77)
-// per (image, channel) mean and max over the pixels.  grid = (B, C/256... ) one thread per channel.
-__global__ void cbam_pool_kernel(const __half* __restrict__ x, float* __restrict__ avg, float* __restrict__ mx, int HW, int C) {
-  const int b = blockIdx.y;
+// per (image, channel) partial sum and max over a slice of the pixels: grid (C/128, B, kPoolSplit)
+constexpr int kPoolSplit = 16;
+__global__ void cbam_pool_kernel(const __half* __restrict__ x, float* __restrict__ psum, float* __restrict__ pmax, int HW, int C) {
+  const int b = blockIdx.y, sp = blockIdx.z;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  const int per = (HW + kPoolSplit - 1) / kPoolSplit;
+  const int i0 = sp * per, i1 = min(HW, i0 + per);
   const __half* p = x + (long long)b * HW * C + c;
   float s = 0.f, m = -CUDART_INF_F;
-  for (int i = 0; i < HW; ++i) {
+  for (int i = i0; i < i1; ++i) {
     const float v = __half2float(p[(long long)i * C]);
     s += v;
     m = fmaxf(m, v);
   }
-  avg[b * C + c] = s / HW;
-  mx[b * C + c] = m;
+  psum[((long long)b * kPoolSplit + sp) * C + c] = s;
+  pmax[((long long)b * kPoolSplit + sp) * C + c] = m;
 }
 // gate[b,c] = sigmoid(mlp(avg) + mlp(max)), mlp = Linear(C,R) -> ReLU -> Linear(R,C); one block per image
-__global__ void cbam_mlp_kernel(const float* __restrict__ avg, const float* __restrict__ mx, const float* __restrict__ w1,
-                                const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-                                float* __restrict__ gate, int C, int R) {
-  extern __shared__ float hid[];  // [2][R]
+__global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int HW,
+                                const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                                const float* __restrict__ b2, float* __restrict__ gate, int C, int R) {
+  extern __shared__ float sm[];  // avg[C] | max[C] | hid[2R]
+  float* avg = sm;
+  float* mx = sm + C;
+  float* hid = sm + 2 * C;
   const int b = blockIdx.x;
-  for (int r = threadIdx.x; r < 2 * R; r += blockDim.x) {
-    const float* src = (r < R ? avg : mx) + b * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, m = -CUDART_INF_F;
+    for (int sp = 0; sp < kPoolSplit; ++sp) {
+      s += psum[((long long)b * kPoolSplit + sp) * C + c];
+      m = fmaxf(m, pmax[((long long)b * kPoolSplit + sp) * C + c]);
+    }
+    avg[c] = s / HW;
+    mx[c] = m;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int r = warp; r < 2 * R; r += nwarp) {  // one warp per hidden unit: coalesced weight rows
+    const float* src = (r < R) ? avg : mx;
     const float* wr = w1 + (long long)(r % R) * C;
-    float a = b1[r % R];
-    for (int c = 0; c < C; ++c) a += wr[c] * src[c];
-    hid[r] = fmaxf(a, 0.f);
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a += wr[c] * src[c];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) hid[r] = fmaxf(a + b1[r % R], 0.f);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -287,16 +310,25 @@ __global__ void cbam_apply_kernel(const __half* __restrict__ x, const float* __r
 
 // ---------------------------------------------------------------- sensory GRU (modules.py:145-149, quirk Q7)
 // values fp16 NHWC [B,HW,3C] = [forget | update | new]; h fp16 [B,HW,C] -> h' = f*h*(1-u) + u*tanh(n)
-__global__ void gru_kernel(const __half* __restrict__ values, const __half* __restrict__ h, __half* __restrict__ out,
-                           long long pixels, int C) {
-  const long long total = pixels * C;
+__global__ void __launch_bounds__(256)
+gru_kernel(const __half* __restrict__ values, const __half* __restrict__ h, __half* __restrict__ out, long long pixels, int C) {
+  const int C8 = C / 8;
+  const long long total = pixels * C8;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const long long p = i / C;
-    const int c = (int)(i - p * C);
-    const __half* v = values + p * 3 * C;
-    const float f = sigmoidf_(__half2float(v[c])), u = sigmoidf_(__half2float(v[C + c])), n = tanhf(__half2float(v[2 * C + c]));
-    const float hv = __half2float(h[i]);
-    out[i] = __float2half_rn(f * hv * (1.f - u) + u * n);
+    const long long p = i / C8;
+    const int c = (int)(i - p * C8) * 8;
+    const __half* v = values + p * 3 * C + c;
+    float f[8], u[8], n[8], hv[8], o[8];
+    ld8(v, f);
+    ld8(v + C, u);
+    ld8(v + 2 * C, n);
+    ld8(h + p * C + c, hv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float fg = sigmoidf_(f[e]), ug = sigmoidf_(u[e]);
+      o[e] = fg * hv[e] * (1.f - ug) + ug * tanhf(n[e]);
+    }
+    st8(out + p * C + c, o, false);
   }
 }
 
@@ -362,6 +394,25 @@ __global__ void up4_softmax_kernel(const float* __restrict__ agg, float* __restr
   for (int k = 0; k < K1; ++k) prob[(long long)k * H * W + i] *= inv;
 }
 
+// 3x3 gather of the fused logit head: z fp32 [B,H,W,9] (z[..., t] = <relu(p4), w_t>) ->
+// logits[b,y,x] = bias + sum_{t=(dy+1)*3+(dx+1)} z[b, y+dy, x+dx, t]  (zero padding)  == Conv2d(256,1,3,pad=1)
+__global__ void head_gather3x3_kernel(const float* __restrict__ z, float* __restrict__ out, float bias, int B, int H, int W) {
+  const long long total = (long long)B * H * W;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int x = (int)(i % W);
+    long long p = i / W;
+    const int y = (int)(p % H);
+    const int b = (int)(p / H);
+    float a = bias;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) a += z[(((long long)b * H + yy) * W + xx) * 9 + t];
+    }
+    out[i] = a;
+  }
+}
+
 // fp16 token-major [n, C] -> fp16 bank rows dst[c, j] (ld_dst): value append from the NHWC encoder output
 __global__ void transpose_append_kernel(const __half* __restrict__ src, __half* __restrict__ dst, long long ld_dst, int n,
                                         int C) {
@@ -397,7 +448,8 @@ int ew_nhwc_to_nchw(const __half* src, float* dst, int B, int C, int H, int W, c
 }
 int ew_stem_im2col(const float* src, __half* dst, __half* dst_lo, int B, int C, int H, int W, int Kp, cudaStream_t s) {
   B200_REQUIRE(H % 2 == 0 && W % 2 == 0 && Kp % 64 == 0 && Kp >= 49 * C, "stem_im2col: bad shape");
-  ew::stem_im2col_kernel<<<grid_of((long long)B * (H / 2) * (W / 2) * Kp), 256, 0, s>>>(src, dst, dst_lo, B, C, H, W, Kp);
+  const int row_elems = (W / 2) * Kp;
+  ew::stem_im2col_kernel<<<dim3(ceil_div(row_elems, 256 * 4), B * (H / 2)), 256, 0, s>>>(src, dst, dst_lo, B, C, H, W, Kp);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -409,7 +461,7 @@ int ew_maxpool(const __half* x, const __half* x_lo, __half* y, __half* y_lo, int
 }
 int ew_up2_add(const __half* g, const __half* skip, __half* raw, __half* relu, int B, int h, int w, int C, cudaStream_t s) {
   B200_REQUIRE(C % 8 == 0, "up2_add: C %% 8");
-  ew::up2_add_kernel<<<grid_of((long long)B * 4 * h * w * (C / 8)), 256, 0, s>>>(g, skip, raw, relu, B, h, w, C);
+  ew::up2_add_kernel<<<dim3(ceil_div(2 * w * (C / 8), 256 * 2), B * 2 * h), 256, 0, s>>>(g, skip, raw, relu, B, h, w, C);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -428,15 +480,15 @@ int ew_area_down_plane(const float* x, float* y, int B, int H, int W, int r, cud
 int ew_cbam(const __half* x, const float* w1, const float* b1, const float* w2, const float* b2, const float* ws,
             const float* bs, float* scratch, __half* raw, __half* relu, int B, int H, int W, int C, int R,
             cudaStream_t s) {
-  // scratch: avg[B*C] | max[B*C] | gate[B*C] | stats[B*H*W*2]
-  float* avg = scratch;
-  float* mx = avg + (long long)B * C;
-  float* gate = mx + (long long)B * C;
+  // scratch: psum[B*16*C] | pmax[B*16*C] | gate[B*C] | stats[B*H*W*2]
+  float* psum = scratch;
+  float* pmax = psum + (long long)B * ew::kPoolSplit * C;
+  float* gate = pmax + (long long)B * ew::kPoolSplit * C;
   float* stats = gate + (long long)B * C;
   const int HW = H * W;
-  ew::cbam_pool_kernel<<<dim3(ceil_div(C, 128), B), 128, 0, s>>>(x, avg, mx, HW, C);
+  ew::cbam_pool_kernel<<<dim3(ceil_div(C, 128), B, ew::kPoolSplit), 128, 0, s>>>(x, psum, pmax, HW, C);
   B200_LAUNCH_CHECK();
-  ew::cbam_mlp_kernel<<<B, 256, 2 * R * sizeof(float), s>>>(avg, mx, w1, b1, w2, b2, gate, C, R);
+  ew::cbam_mlp_kernel<<<B, 256, (2 * C + 2 * R) * sizeof(float), s>>>(psum, pmax, HW, w1, b1, w2, b2, gate, C, R);
   B200_LAUNCH_CHECK();
   const long long warps = (long long)B * HW;
   ew::cbam_stats_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, gate, stats, B, HW, C);
@@ -446,7 +498,8 @@ int ew_cbam(const __half* x, const float* w1, const float* b1, const float* w2, 
   return 0;
 }
 int ew_gru(const __half* values, const __half* h, __half* out, long long pixels, int C, cudaStream_t s) {
-  ew::gru_kernel<<<grid_of(pixels * C), 256, 0, s>>>(values, h, out, pixels, C);
+  B200_REQUIRE(C % 8 == 0, "gru: C %% 8");
+  ew::gru_kernel<<<grid_of(pixels * (C / 8)), 256, 0, s>>>(values, h, out, pixels, C);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -459,6 +512,11 @@ int ew_output_tail(const float* logits, float* agg, float* prob, float* logits_o
   ew::aggregate_kernel<<<ceil_div(h * w, 256), 256, 0, s>>>(logits, agg, K, h * w);
   B200_LAUNCH_CHECK();
   ew::up4_softmax_kernel<<<ceil_div(16ll * h * w, 256), 256, 0, s>>>(agg, prob, logits_out, K + 1, h, w);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_head_gather3x3(const float* z, float* out, float bias, int B, int H, int W, cudaStream_t s) {
+  ew::head_gather3x3_kernel<<<grid_of((long long)B * H * W), 256, 0, s>>>(z, out, bias, B, H, W);
   B200_LAUNCH_CHECK();
   return 0;
 }

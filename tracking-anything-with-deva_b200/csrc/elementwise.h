@@ -16,5 +16,6 @@ int ew_cbam(const __half* x, const float* w1, const float* b1, const float* w2, 
 int ew_gru(const __half* values, const __half* h, __half* out, long long pixels, int C, cudaStream_t s);
 int ew_key_tail(const float* y, int ld, int Q, int CK, float* key, float* shr, float* sel, cudaStream_t s);
 int ew_output_tail(const float* logits, float* agg, float* prob, float* logits_out, int K, int h, int w, cudaStream_t s);
+int ew_head_gather3x3(const float* z, float* out, float bias, int B, int H, int W, cudaStream_t s);
 int ew_transpose_append(const __half* src, __half* dst, long long ld_dst, int n, int C, cudaStream_t s);
 }  // namespace b200

@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libdeva_b200.so')
-ABI_VERSION = 3
+ABI_VERSION = 4
 LIST_PITCH = 32
 MAX_GROUPS = 256
 
@@ -27,7 +27,8 @@ class ConvDesc(ctypes.Structure):
                 ('bias', c_void_p), ('res', c_void_p), ('res_lo', c_void_p), ('res_broadcast', c_int32),
                 ('rank1_w', c_void_p), ('rank1_x', c_void_p),
                 ('out_raw', c_void_p), ('out_relu', c_void_p), ('out_f32', c_void_p),
-                ('out_raw_lo', c_void_p), ('out_relu_lo', c_void_p)]
+                ('out_raw_lo', c_void_p), ('out_relu_lo', c_void_p),
+                ('head_w', c_void_p), ('head_out', c_void_p), ('head_n', c_int32)]
 
 
 _SIGNATURES = {
@@ -66,6 +67,7 @@ _SIGNATURES = {
     'deva_b200_gru': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     'deva_b200_key_tail': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'deva_b200_output_tail': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'deva_b200_head_gather3x3': (c_int, [c_void_p, c_void_p, ctypes.c_float, c_int, c_int, c_int, c_void_p]),
     'deva_b200_transpose_append': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES.keys())
@@ -190,10 +192,10 @@ def _p(t):
 
 def conv2d(x, batch, h, w, cin_pad, w_packed, kh, stride, cout, cout_pad, nt, th, tw, bias, x2=None, x_lo=None, res=None,
            res_lo=None, res_broadcast=False, rank1_w=None, rank1_x=None, out_raw=None, out_relu=None, out_f32=None,
-           out_raw_lo=None, out_relu_lo=None):
+           out_raw_lo=None, out_relu_lo=None, head_w=None, head_out=None, head_n=0):
     d = ConvDesc(_p(x), _p(x2), _p(x_lo), batch, h, w, cin_pad, _p(w_packed), kh, kh, stride, cout, cout_pad, nt, th, tw,
                  _p(bias), _p(res), _p(res_lo), int(res_broadcast), _p(rank1_w), _p(rank1_x), _p(out_raw), _p(out_relu),
-                 _p(out_f32), _p(out_raw_lo), _p(out_relu_lo))
+                 _p(out_f32), _p(out_raw_lo), _p(out_relu_lo), _p(head_w), _p(head_out), head_n)
     _check(lib().deva_b200_conv2d(ctypes.byref(d), _stream()), 'conv2d')
 
 
@@ -247,3 +249,7 @@ def output_tail(logits, agg, prob, logits_out, k, h, w):
 
 def transpose_append(src, dst, ld_dst, n, c):
     _check(lib().deva_b200_transpose_append(_ptr(src), _ptr(dst), ld_dst, n, c, _stream()), 'transpose_append')
+
+
+def head_gather3x3(z, out, bias, b, h, w):
+    _check(lib().deva_b200_head_gather3x3(_ptr(z), _ptr(out), float(bias), b, h, w, _stream()), 'head_gather3x3')

@@ -47,10 +47,13 @@ class NativeEngine:
         L = t.layers
         P: Dict[str, ops.PackedConv] = {}
         for name, spec in L.items():
-            # The key path (pixel encoder -> key projection) and the final logit conv run in split precision
-            # (fp16 hi/lo pairs, ~fp32 accuracy): the top-k read and the sigmoid are discontinuous / steep in
-            # exactly these quantities, and together they are < 3 % of the frame's FLOPs.
-            precise = name.startswith('pixel_encoder') or name.startswith('key_proj') or name.endswith('.pred')
+            # The key path (pixel encoder -> key projection) runs in split precision (fp16 hi/lo pairs, ~fp32
+            # accuracy): the top-k read is discontinuous in the keys, and the path is < 3 % of the frame's FLOPs.
+            precise = name.startswith('pixel_encoder') or name.startswith('key_proj')
+            if name.endswith('.pred'):  # folded into up_8_4.c2's epilogue as a fp32 9-tap head (see decode)
+                self.pred_w = spec.weight[0].permute(1, 2, 0).reshape(9, -1).float().contiguous()  # [tap, cin]
+                self.pred_b = float(spec.bias[0])
+                continue
             if name.endswith('.stem'):
                 P[name] = ops.pack_stem(spec.weight, spec.bias, precise=True)
             elif name.endswith('.stem_img') or name.endswith('.stem_mask'):
@@ -212,9 +215,12 @@ class NativeEngine:
             g4_raw, g4_relu = ops.up2_add(p8, skip4)
             q = p + '.up_8_4.out_conv'
             y = ops.conv(g4_relu, P[q + '.c1'], want_relu=True)
-            o4 = ops.conv_ex(y, P[q + '.c2'], res=g4_raw, want_raw=True, want_relu=True, want_lo=True)
+            # p4 = c2(...) + g4; the logit conv pred(relu(p4)) (big_modules.py:189-190) is folded in: the epilogue
+            # emits the 9 per-tap dot products in fp32, a 3x3 gather finishes the convolution.
+            o4 = ops.conv_ex(y, P[q + '.c2'], res=g4_raw, want_raw=True, head_w=self.pred_w)
             p4_raw = o4.raw
-            logits = ops.conv_ex(o4.relu, P[p + '.pred'], x_lo=o4.relu_lo, want_f32=True).f32  # [k,4h,4w,1] fp32
+            logits = torch.empty(o4.head.shape[0], 4 * hh, 4 * ww, 1, dtype=torch.float32, device=o4.head.device)
+            nat.head_gather3x3(o4.head, logits, self.pred_b, o4.head.shape[0], 4 * hh, 4 * ww)
             logits_all.append(logits)
             if update_sensory:
                 g = ops.conv(p16, P[p + '.su.g16_conv'], want_raw=True)

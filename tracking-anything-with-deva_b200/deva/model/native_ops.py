@@ -81,16 +81,16 @@ class PackedConv:
 
 
 class ConvOut:
-    __slots__ = ('raw', 'raw_lo', 'relu', 'relu_lo', 'f32')
+    __slots__ = ('raw', 'raw_lo', 'relu', 'relu_lo', 'f32', 'head')
 
     def __init__(self):
-        self.raw = self.raw_lo = self.relu = self.relu_lo = self.f32 = None
+        self.raw = self.raw_lo = self.relu = self.relu_lo = self.f32 = self.head = None
 
 
 def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = None, x_lo: Optional[torch.Tensor] = None,
             res: Optional[torch.Tensor] = None, res_lo: Optional[torch.Tensor] = None,
             rank1_x: Optional[torch.Tensor] = None, want_raw: bool = False, want_relu: bool = False,
-            want_f32: bool = False, want_lo: bool = False) -> ConvOut:
+            want_f32: bool = False, want_lo: bool = False, head_w: Optional[torch.Tensor] = None) -> ConvOut:
     """x fp16 NHWC [B,H,W,cin_pad] (+ x2: implicit channel concat, or + x_lo: split precision) -> ConvOut."""
     assert x.dtype == torch.float16 and x.is_contiguous() and x.shape[-1] == pc.cin_pad, (x.shape, pc.cin_pad)
     assert (x2 is not None) == pc.two_inputs and (x_lo is not None) == pc.precise
@@ -122,10 +122,15 @@ def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = Non
         assert res_lo is None or (res_lo.shape == res.shape and res_lo.is_contiguous())
     if pc.rank1_w is not None:
         assert rank1_x is not None and rank1_x.dtype == torch.float32 and rank1_x.numel() == b * ho * wo
+    head_n = 0
+    if head_w is not None:  # fused 1x1 head on relu(result): [head_n, cout] fp32
+        head_n = head_w.shape[0]
+        assert head_w.dtype == torch.float32 and head_w.is_contiguous() and head_w.shape[1] == pc.cout
+        o.head = torch.empty(b, ho, wo, head_n, dtype=torch.float32, device=dev)
     nat.conv2d(x, b, h, w, pc.cin_pad, pc.w_packed, pc.k, pc.stride, pc.cout, pc.cout_pad, pc.nt, th, tw, pc.bias,
                x2=x2, x_lo=x_lo, res=res, res_lo=res_lo, res_broadcast=res_b, rank1_w=pc.rank1_w,
                rank1_x=rank1_x if pc.rank1_w is not None else None, out_raw=o.raw, out_relu=o.relu, out_f32=o.f32,
-               out_raw_lo=o.raw_lo, out_relu_lo=o.relu_lo)
+               out_raw_lo=o.raw_lo, out_relu_lo=o.relu_lo, head_w=head_w, head_out=o.head, head_n=head_n)
     return o
 
 
@@ -192,7 +197,7 @@ def cbam_residual(x: torch.Tensor, params: dict, want_raw=True, want_relu=True):
     """x + CBAM(x) on fp16 NHWC; params: w1,b1,w2,b2 (channel MLP), ws [2*49], bs [1] (fp32)."""
     b, h, w, c = x.shape
     r = params['w1'].shape[0]
-    scratch = torch.empty(3 * b * c + 2 * b * h * w, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(33 * b * c + 2 * b * h * w, dtype=torch.float32, device=x.device)
     raw = torch.empty_like(x) if want_raw else None
     relu = torch.empty_like(x) if want_relu else None
     nat.cbam(x, params['w1'], params['b1'], params['w2'], params['b2'], params['ws'], params['bs'], scratch, raw, relu,
