@@ -247,7 +247,7 @@ def run_ours(args):
             'metric': METRIC, 'value': world * args.steps / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16 operands / f32 accumulate '
-            '(memory read); f32 (conv stack, cuDNN interim)', 'data': 'synthetic',
+            '(tcgen05 memory read + conv stack); key path split-f16x3 (~f32)', 'data': 'synthetic',
             'config': {'workload': wl['name'], 'frame': [wl['h'], wl['w']], 'query_positions': clip.q,
                        'objects': wl['k'], 'memory_slots': wl['n'], 'mem_every': 5, 'top_k': TOP_K,
                        'parallelism': f'clip-parallel x{world}' if world > 1 else 'single clip',

@@ -21,7 +21,7 @@ def _core(cfg, sd, backend):
 
 # 'native': every layer on the hand-written sm_100a kernels (fp16 activations, fp32 accumulate);
 # 'torch': the same graphs through cuDNN fp32 (isolates the memory-read kernels).
-@pytest.mark.parametrize('backend,tol', [('native', 2e-3), ('torch', 1e-3)])
+@pytest.mark.parametrize('backend,tol', [('native', 2.5e-3), ('torch', 1e-3)])
 def test_vos_clip_matches_reference(golden_dir, synthetic_sd, backend, tol):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
