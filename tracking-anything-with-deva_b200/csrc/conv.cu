@@ -42,7 +42,6 @@ struct Params {
   int tiles_x, tiles_y, tw, th;
   int n_tiles, nt;
   int taps, cblocks;
-  int pos_x, pos_y, pos_b;  // which TMA coordinate carries x / y / image index
   signed char tap_map[kMaxTaps], tap_w[kMaxTaps], tap_dx[kMaxTaps], tap_dy[kMaxTaps];  // per k-entry: activation
                                                          // map, weight tap group, input offset
   const float* bias;
@@ -109,8 +108,10 @@ __device__ __forceinline__ void tile_decode(int tile, const Params& p, int& b, i
 
 __global__ void __launch_bounds__(THREADS, 1)
 conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128B swizzle atoms) comes from the declaration: deriving an aligned pointer through an
+  // integer cast would make the compiler lose the shared address space (generic LD/ST instead of LDS/STS).
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -148,10 +149,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
         int b, y0, x0, n0;
         tile_decode(tile, p, b, y0, x0, n0);
         for (int t = 0; t < p.taps; ++t) {
-          int c[5] = {0, 0, 0, 0, 0};
-          c[p.pos_x] = x0 + p.tap_dx[t];
-          c[p.pos_y] = y0 + p.tap_dy[t];
-          c[p.pos_b] = b;
+          int c[5] = {0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b, 0};  // (channel, x, y, image, 1)
           const CUtensorMap* am = &maps.act[p.tap_map[t]];
           for (int cb = 0; cb < p.cblocks; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -273,23 +271,23 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
             store_split(v, p.out_raw, p.out_raw_lo, off + c * 32, false);
             store_split(v, p.out_relu, p.out_relu_lo, off + c * 32, true);
             if (p.head_w) {
+              float rv[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) rv[j] = fmaxf(v[j], 0.f);
 #pragma unroll
               for (int t = 0; t < kMaxHead; ++t) {
                 const float4* w4 = reinterpret_cast<const float4*>(s_head + t * 256 + c * 32);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four independent chains per tap
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const float4 wv = w4[j];
-                  hacc[t] = fmaf(fmaxf(v[4 * j], 0.f), wv.x, hacc[t]);
-                  hacc[t] = fmaf(fmaxf(v[4 * j + 1], 0.f), wv.y, hacc[t]);
-                  hacc[t] = fmaf(fmaxf(v[4 * j + 2], 0.f), wv.z, hacc[t]);
-                  hacc[t] = fmaf(fmaxf(v[4 * j + 3], 0.f), wv.w, hacc[t]);
+                  a0 = fmaf(rv[4 * j], wv.x, a0);
+                  a1 = fmaf(rv[4 * j + 1], wv.y, a1);
+                  a2 = fmaf(rv[4 * j + 2], wv.z, a2);
+                  a3 = fmaf(rv[4 * j + 3], wv.w, a3);
                 }
+                hacc[t] += (a0 + a1) + (a2 + a3);
               }
-            }
-            if (p.out_f32) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(p.out_f32 + off + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           } else {  // ragged channel tail (e.g. Cout = 1, 129): scalar path
 #pragma unroll
@@ -321,7 +319,9 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (p.head_w && live) {
-        for (int t = 0; t < p.head_n; ++t) p.head_out[pix * p.head_n + t] = hacc[t];
+#pragma unroll
+        for (int t = 0; t < kMaxHead; ++t)
+          if (t < p.head_n) p.head_out[pix * p.head_n + t] = hacc[t];
       }
     }
   }
@@ -412,7 +412,6 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   p.tiles_x = ceil_div(wo, d.tw); p.tiles_y = ceil_div(ho, d.th);
   p.nt = d.nt; p.n_tiles = d.cout_pad / d.nt;
   p.cblocks = d.cin_pad / 64;
-  p.pos_x = 1; p.pos_y = 2; p.pos_b = 3;
   p.bias = d.bias;
   p.res = reinterpret_cast<const __half*>(d.res);
   p.res_lo = reinterpret_cast<const __half*>(d.res_lo);

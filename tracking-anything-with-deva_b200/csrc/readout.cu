@@ -52,8 +52,10 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
 __global__ void __launch_bounds__(THREADS, 1)
 readout_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_p,
                const __grid_constant__ Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128B swizzle atoms) comes from the declaration: deriving an aligned pointer through an
+  // integer cast would make the compiler lose the shared address space (generic LD/ST instead of LDS/STS).
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);

@@ -100,8 +100,10 @@ __global__ void __launch_bounds__(THREADS, 1)
 simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_ql,
                const __grid_constant__ CUtensorMap map_kh, const __grid_constant__ CUtensorMap map_kl,
                const __grid_constant__ Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128B swizzle atoms) comes from the declaration: deriving an aligned pointer through an
+  // integer cast would make the compiler lose the shared address space (generic LD/ST instead of LDS/STS).
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;                                   // [hi/lo][kb] tiles
   uint8_t* sK = smem + Q_BYTES;                         // [stage][hi/lo][kb] tiles
   float* list_val = reinterpret_cast<float*>(sK + KSTAGES * KSTAGE_BYTES);   // [kListCap][BQ]
