@@ -218,16 +218,33 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       for (int t = 0; t < kMaxHead; ++t) hacc[t] = 0.f;
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
+      // Software pipeline over 32-channel chunks: the TMEM load and the residual loads of chunk c+1 are in flight
+      // while chunk c is finished (the residual comes from L2/HBM: ~1 us if waited for in place).
+      const int n_chunks = p.nt / 32;
+      const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + acc * 256;
+      const bool res_pf = res && live && vec_ok && (p.cout % 32 == 0);
+      uint32_t r[32];
+      uint4 res_cur[4], res_nxt[4];
+      tmem_ld_32x32(t_addr, r);
+      if (res_pf) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res_cur[j] = *reinterpret_cast<const uint4*>(res + j * 8);
+      }
 #pragma unroll 1
-      for (int c = 0; c < p.nt / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + acc * 256 + c * 32, r);
+      for (int c = 0; c < n_chunks; ++c) {
         tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (c + 1 < n_chunks) {
+          tmem_ld_32x32(t_addr + (c + 1) * 32, r);
+          if (res_pf && n0 + (c + 2) * 32 <= p.cout) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res_nxt[j] = *reinterpret_cast<const uint4*>(res + (c + 1) * 32 + j * 8);
+          }
+        }
         const int ch0 = n0 + c * 32;
         if (live && ch0 < p.cout) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (ch0 + 32 <= p.cout && vec_ok) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -245,7 +262,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
             if (res) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(res + c * 32 + j);
+                const uint4 rv = res_pf ? res_cur[j / 8] : *reinterpret_cast<const uint4*>(res + c * 32 + j);
                 const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -289,6 +306,11 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
                 hacc[t] += (a0 + a1) + (a2 + a3);
               }
             }
+            if (p.out_f32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(p.out_f32 + off + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
           } else {  // ragged channel tail (e.g. Cout = 1, 129): scalar path
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -314,6 +336,8 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
             }
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res_cur[j] = res_nxt[j];
       }
       tc_fence_before();
       __syncwarp();
