@@ -24,15 +24,18 @@
 namespace b200 {
 namespace simtopk {
 
-constexpr int BQ = 128, BNK = 128, BK = 64;
-constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 halves
-constexpr int MAX_KB = 2;              // 2*CK/64 with CK <= 64
-constexpr int KSTAGES = 2;
-constexpr int THREADS = 192;
-constexpr int Q_BYTES = 2 * MAX_KB * TILE_BYTES;            // hi/lo x k-blocks
-constexpr int KSTAGE_BYTES = 2 * MAX_KB * TILE_BYTES;
-constexpr int LIST_BYTES = 2 * kListCap * BQ * 4;
-constexpr int NS_BYTES = 2 * BNK * 4;
+constexpr int BQ = 128, BNK = 64, BK = 64;
+constexpr int QTILE_BYTES = BQ * 128;   // 128 query rows x 64 halves
+constexpr int KTILE_BYTES = BNK * 128;  // 64 key rows x 64 halves
+constexpr int MAX_KB = 2;               // 2*CK/64 with CK <= 64
+constexpr int KSTAGES = 3;
+constexpr int ACC_STAGES = 4;           // 4 x 64 TMEM columns; epilogue group g owns stages g, g+2
+constexpr int GROUPS = 2;               // epilogue warp groups working on alternating tiles
+constexpr int THREADS = 64 + GROUPS * 128;
+constexpr int Q_BYTES = 2 * MAX_KB * QTILE_BYTES;  // hi/lo x k-blocks
+constexpr int KSTAGE_BYTES = 2 * MAX_KB * KTILE_BYTES;
+constexpr int LIST_BYTES = GROUPS * 2 * kListCap * BQ * 4;
+constexpr int NS_BYTES = ACC_STAGES * BNK * 4;
 constexpr int SMEM_BYTES = Q_BYTES + KSTAGES * KSTAGE_BYTES + LIST_BYTES + NS_BYTES + 256 + 1024;
 
 struct Params {
@@ -41,45 +44,11 @@ struct Params {
   int qpad;
   const float* neg_s;   // [n_window]  -shrinkage/sqrt(CK)
   const float* bsq;     // [q]
-  float* part_val;      // [nsplit][kListCap][qpad]
+  float* part_val;      // [nsplit*GROUPS][kListCap][qpad]
   int* part_idx;
   float* dense_out;     // DENSE mode: [q][ld_dense]
   long long ld_dense;
 };
-
-
-// Replace the current minimum of this thread's candidate column with (v, n) and find the new minimum.
-// The column has kListCap entries (entries >= top_k hold +inf).  All 32 loads are issued back to back
-// and reduced with a 5-level tree, so one insertion costs ~one shared-memory latency instead of 32.
-struct MinSlot { float thr; int pos; };
-__device__ __noinline__ MinSlot insert_candidate(float* list_val, int* list_idx, int row, float v, int n,
-                                                 int minpos) {
-  list_val[minpos * BQ + row] = v;
-  list_idx[minpos * BQ + row] = n;
-  float x[kListCap];
-  int pos[kListCap / 2];
-#pragma unroll
-  for (int j = 0; j < kListCap; ++j) x[j] = list_val[j * BQ + row];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const bool c = x[j + 16] < x[j];
-    x[j] = c ? x[j + 16] : x[j];
-    pos[j] = c ? j + 16 : j;
-  }
-#pragma unroll
-  for (int w = 8; w >= 1; w >>= 1) {
-#pragma unroll
-    for (int j = 0; j < w; ++j) {
-      const bool c = x[j + w] < x[j];
-      x[j] = c ? x[j + w] : x[j];
-      pos[j] = c ? pos[j + w] : pos[j];
-    }
-  }
-  MinSlot r;
-  r.thr = x[0];
-  r.pos = pos[0];
-  return r;
-}
 
 // v[j] for a run-time j without spilling v to local memory: 5-level select tree (31 selects).
 __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
@@ -95,6 +64,43 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
   return (j & 1) ? d[1] : d[0];
 }
 
+// Per-thread running top-k: kListCap (32) candidate slots in a shared-memory column (entries >= top_k hold
+// +inf), tracked as 4 groups of 8 with the group minima (value, position) in registers.  Replacing the global
+// minimum re-scans only its group: 8 shared loads + a handful of selects per insertion.
+struct TopK {
+  float gmin[4];
+  int gpos[4];
+  float thr;
+  int minpos;
+  __device__ __forceinline__ void refresh() {
+    float m01 = gmin[0]; int p01 = gpos[0];
+    if (gmin[1] < m01) { m01 = gmin[1]; p01 = gpos[1]; }
+    float m23 = gmin[2]; int p23 = gpos[2];
+    if (gmin[3] < m23) { m23 = gmin[3]; p23 = gpos[3]; }
+    const bool c = m23 < m01;
+    thr = c ? m23 : m01;
+    minpos = c ? p23 : p01;
+  }
+  __device__ __forceinline__ void insert(float* lv, int* li, int row, float v, int n) {
+    lv[minpos * BQ + row] = v;
+    li[minpos * BQ + row] = n;
+    const int g = minpos >> 3;
+    const float* base = lv + (g * 8) * BQ + row;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = base[e * BQ];
+    float m = x[0]; int mp = 0;
+#pragma unroll
+    for (int e = 1; e < 8; ++e)
+      if (x[e] < m) { m = x[e]; mp = e; }
+    mp += g * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i == g) { gmin[i] = m; gpos[i] = mp; }
+    refresh();
+  }
+};
+
 template <bool DENSE>
 __global__ void __launch_bounds__(THREADS, 1)
 simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_ql,
@@ -104,32 +110,31 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
   // integer cast would make the compiler lose the shared address space (generic LD/ST instead of LDS/STS).
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sQ = smem;                                   // [hi/lo][kb] tiles
-  uint8_t* sK = smem + Q_BYTES;                         // [stage][hi/lo][kb] tiles
-  float* list_val = reinterpret_cast<float*>(sK + KSTAGES * KSTAGE_BYTES);   // [kListCap][BQ]
-  int* list_idx = reinterpret_cast<int*>(list_val + kListCap * BQ);
-  float* ns = reinterpret_cast<float*>(list_idx + kListCap * BQ);            // [2][BNK]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ns + 2 * BNK);
+  uint8_t* sQ = smem;                                   // [hi/lo][kb] query tiles, resident
+  uint8_t* sK = smem + Q_BYTES;                         // [stage][hi/lo][kb] key tiles
+  float* list_val = reinterpret_cast<float*>(sK + KSTAGES * KSTAGE_BYTES);   // [group][kListCap][BQ]
+  int* list_idx = reinterpret_cast<int*>(list_val + GROUPS * kListCap * BQ);
+  float* ns = reinterpret_cast<float*>(list_idx + GROUPS * kListCap * BQ);   // [ACC_STAGES][BNK]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ns + ACC_STAGES * BNK);
   uint64_t* q_full = bars;
-  uint64_t* full = bars + 1;            // [KSTAGES]
-  uint64_t* empty = full + KSTAGES;     // [KSTAGES]
-  uint64_t* acc_full = empty + KSTAGES; // [2]
-  uint64_t* acc_empty = acc_full + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* full = bars + 1;                    // [KSTAGES]
+  uint64_t* empty = full + KSTAGES;             // [KSTAGES]
+  uint64_t* acc_full = empty + KSTAGES;         // [ACC_STAGES]
+  uint64_t* acc_empty = acc_full + ACC_STAGES;  // [ACC_STAGES]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ;
   const int t_begin = blockIdx.y * p.tiles_per_split;
   const int t_end = min(p.tiles_total, t_begin + p.tiles_per_split);
-  const uint32_t op_bytes = 2u * p.kblocks * TILE_BYTES;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_qh); tma_prefetch_desc(&map_ql);
     tma_prefetch_desc(&map_kh); tma_prefetch_desc(&map_kl);
     mbar_init(q_full, 1);
     for (int i = 0; i < KSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -140,20 +145,20 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, op_bytes);
+      mbar_expect_tx(q_full, 2u * p.kblocks * QTILE_BYTES);
       for (int kb = 0; kb < p.kblocks; ++kb) {
-        tma_load_2d(sQ + (0 * MAX_KB + kb) * TILE_BYTES, &map_qh, q_full, kb * BK, q0);
-        tma_load_2d(sQ + (1 * MAX_KB + kb) * TILE_BYTES, &map_ql, q_full, kb * BK, q0);
+        tma_load_2d(sQ + (0 * MAX_KB + kb) * QTILE_BYTES, &map_qh, q_full, kb * BK, q0);
+        tma_load_2d(sQ + (1 * MAX_KB + kb) * QTILE_BYTES, &map_ql, q_full, kb * BK, q0);
       }
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], op_bytes);
+        mbar_expect_tx(&full[stage], 2u * p.kblocks * KTILE_BYTES);
         uint8_t* dst = sK + stage * KSTAGE_BYTES;
         for (int kb = 0; kb < p.kblocks; ++kb) {
-          tma_load_2d(dst + (0 * MAX_KB + kb) * TILE_BYTES, &map_kh, &full[stage], kb * BK, t * BNK);
-          tma_load_2d(dst + (1 * MAX_KB + kb) * TILE_BYTES, &map_kl, &full[stage], kb * BK, t * BNK);
+          tma_load_2d(dst + (0 * MAX_KB + kb) * KTILE_BYTES, &map_kh, &full[stage], kb * BK, t * BNK);
+          tma_load_2d(dst + (1 * MAX_KB + kb) * KTILE_BYTES, &map_kl, &full[stage], kb * BK, t * BNK);
         }
         if (++stage == KSTAGES) { stage = 0; phase ^= 1; }
       }
@@ -166,8 +171,8 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
       uint32_t phase = 0;
       int it = 0;
       for (int t = t_begin; t < t_end; ++t, ++it) {
-        const int acc = it & 1;
-        mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
+        const int acc = it & (ACC_STAGES - 1);
+        mbar_wait(&acc_empty[acc], ((it / ACC_STAGES) & 1) ^ 1);
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BNK;
@@ -176,10 +181,10 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
         for (int kb = 0; kb < p.kblocks; ++kb) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t qh = umma_desc_sw128(q_base + (0 * MAX_KB + kb) * TILE_BYTES + k * 32);
-            const uint64_t ql = umma_desc_sw128(q_base + (1 * MAX_KB + kb) * TILE_BYTES + k * 32);
-            const uint64_t kh = umma_desc_sw128(k_base + (0 * MAX_KB + kb) * TILE_BYTES + k * 32);
-            const uint64_t kl = umma_desc_sw128(k_base + (1 * MAX_KB + kb) * TILE_BYTES + k * 32);
+            const uint64_t qh = umma_desc_sw128(q_base + (0 * MAX_KB + kb) * QTILE_BYTES + k * 32);
+            const uint64_t ql = umma_desc_sw128(q_base + (1 * MAX_KB + kb) * QTILE_BYTES + k * 32);
+            const uint64_t kh = umma_desc_sw128(k_base + (0 * MAX_KB + kb) * KTILE_BYTES + k * 32);
+            const uint64_t kl = umma_desc_sw128(k_base + (1 * MAX_KB + kb) * KTILE_BYTES + k * 32);
             umma_f16(d_tmem, ql, kh, idesc, (kb | k) != 0);
             umma_f16(d_tmem, qh, kl, idesc, 1);
             umma_f16(d_tmem, qh, kh, idesc, 1);
@@ -191,29 +196,36 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
       }
     }
   } else {
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;  // query within the tile == TMEM lane
+    const int group = (warp - 2) >> 2;  // 0: even local tiles, 1: odd local tiles
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;   // query within the tile == TMEM lane
     const int qg = q0 + row;
     const float bsq = (qg < p.q) ? p.bsq[qg] : 0.f;
     const int top_k = p.top_k;
-    float thr = -CUDART_INF_F;
-    int minpos = 0;
+    float* lv = list_val + group * kListCap * BQ;
+    int* li = list_idx + group * kListCap * BQ;
+    TopK tk;
     if (!DENSE) {
       for (int j = 0; j < kListCap; ++j) {
-        list_val[j * BQ + row] = (j < top_k) ? -CUDART_INF_F : CUDART_INF_F;
-        list_idx[j * BQ + row] = -1;
+        lv[j * BQ + row] = (j < top_k) ? -CUDART_INF_F : CUDART_INF_F;
+        li[j * BQ + row] = -1;
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        tk.gmin[i] = (i * 8 < top_k) ? -CUDART_INF_F : CUDART_INF_F;
+        tk.gpos[i] = i * 8;
+      }
+      tk.refresh();
     }
-    int it = 0;
-    for (int t = t_begin; t < t_end; ++t, ++it) {
-      const int acc = it & 1;
-      const int n0 = t * BNK;
-      {
+    for (int it = group; t_begin + it < t_end; it += GROUPS) {
+      const int acc = it & (ACC_STAGES - 1);
+      const int n0 = (t_begin + it) * BNK;
+      if (row < BNK) {
         const int n = n0 + row;
         ns[acc * BNK + row] = (n >= p.n_lead && n < p.n_window) ? p.neg_s[n] : -CUDART_INF_F;
       }
-      named_bar_sync(1, 128);
-      mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      named_bar_sync(1 + group, 128);
+      mbar_wait(&acc_full[acc], (it / ACC_STAGES) & 1);
       tc_fence_after();
       const float4* ns4 = reinterpret_cast<const float4*>(ns + acc * BNK);
 #pragma unroll 1
@@ -243,17 +255,13 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
           // max-per-lane insertions per chunk, not for every distinct column position.
           uint32_t pending = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pending |= (v[j] > thr) ? (1u << j) : 0u;
+          for (int j = 0; j < 32; ++j) pending |= (v[j] > tk.thr) ? (1u << j) : 0u;
           while (__any_sync(0xffffffffu, pending != 0)) {
             if (pending) {
               const int j = __ffs(pending) - 1;
               pending &= pending - 1;
               const float x = pick32(v, j);
-              if (x > thr) {
-                const MinSlot ms = insert_candidate(list_val, list_idx, row, x, n0 + c * 32 + j, minpos);
-                thr = ms.thr;
-                minpos = ms.pos;
-              }
+              if (x > tk.thr) tk.insert(lv, li, row, x, n0 + c * 32 + j);
             }
           }
         }
@@ -263,10 +271,10 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
     if (!DENSE) {
-      const long long base = (long long)blockIdx.y * kListCap;
+      const long long base = ((long long)blockIdx.y * GROUPS + group) * kListCap;
       for (int j = 0; j < top_k; ++j) {
-        p.part_val[(base + j) * p.qpad + qg] = list_val[j * BQ + row];
-        p.part_idx[(base + j) * p.qpad + qg] = list_idx[j * BQ + row];
+        p.part_val[(base + j) * p.qpad + qg] = lv[j * BQ + row];
+        p.part_idx[(base + j) * p.qpad + qg] = li[j * BQ + row];
       }
     }
   }
@@ -285,19 +293,23 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32)
 merge_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int nsplit, int top_k, int q,
              int qpad, int* __restrict__ out_idx, float* __restrict__ out_w, __half* __restrict__ P, long long ldP,
              float* __restrict__ use_cnt, int n_long, int add_long, int add_work) {
-  __shared__ float cv[MERGE_WARPS][kMaxSplit * kListCap];
-  __shared__ int ci[MERGE_WARPS][kMaxSplit * kListCap];
+  __shared__ float cv[MERGE_WARPS][kMaxSplit * GROUPS * kListCap];
+  __shared__ int ci[MERGE_WARPS][kMaxSplit * GROUPS * kListCap];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qi = blockIdx.x * MERGE_WARPS + w;
-  if (qi >= q) return;
+  const int qb = blockIdx.x * MERGE_WARPS;
   const int C = nsplit * top_k;
-  for (int c = lane; c < C; c += 32) {
-    const int s = c / top_k, j = c - s * top_k;
-    const long long off = ((long long)s * kListCap + j) * qpad + qi;
-    cv[w][c] = part_val[off];
-    ci[w][c] = part_idx[off];
+  // cooperative, sector-coalesced staging of the [C candidates] x [8 queries] tile (rows are qpad apart)
+  for (int i = threadIdx.x; i < C * MERGE_WARPS; i += MERGE_WARPS * 32) {
+    const int c = i / MERGE_WARPS, qo = i - c * MERGE_WARPS;
+    const int s_ = c / top_k, j = c - s_ * top_k;
+    const long long off = ((long long)s_ * kListCap + j) * qpad + qb + qo;
+    const bool ok = qb + qo < q;
+    cv[qo][c] = ok ? part_val[off] : -CUDART_INF_F;
+    ci[qo][c] = ok ? part_idx[off] : -1;
   }
-  __syncwarp();
+  __syncthreads();
+  const int qi = qb + w;
+  if (qi >= q) return;
   float sel_v = -CUDART_INF_F;
   int sel_i = 0;
   for (int round = 0; round < top_k; ++round) {
@@ -390,8 +402,8 @@ static int make_maps(CUtensorMap* m, const __half* q_hi, const __half* q_lo, int
   const uint64_t kdim = 2ull * ck;
   if (make_tmap_2d(&m[0], TmapType::F16, q_hi, kdim, q, kdim * 2, 64, 128, &err) ||
       make_tmap_2d(&m[1], TmapType::F16, q_lo, kdim, q, kdim * 2, 64, 128, &err) ||
-      make_tmap_2d(&m[2], TmapType::F16, k_hi, kdim, n_window, kdim * 2, 64, 128, &err) ||
-      make_tmap_2d(&m[3], TmapType::F16, k_lo, kdim, n_window, kdim * 2, 64, 128, &err)) {
+      make_tmap_2d(&m[2], TmapType::F16, k_hi, kdim, n_window, kdim * 2, 64, 64, &err) ||
+      make_tmap_2d(&m[3], TmapType::F16, k_lo, kdim, n_window, kdim * 2, 64, 64, &err)) {
     set_error("simtopk: %s", err ? err : "tensor map");
     return 3;
   }
@@ -415,7 +427,7 @@ static int choose_split(int q_tiles, int tiles, int max_split) {
 
 size_t simtopk_workspace_bytes(int q) {
   const size_t qpad = (size_t)ceil_div(q, 128) * 128;
-  return (size_t)kMaxSplit * kListCap * qpad * 8;
+  return (size_t)kMaxSplit * simtopk::GROUPS * kListCap * qpad * 8;
 }
 
 int launch_sim_topk(const __half* k_hi, const __half* k_lo, const float* neg_s, int n_window, int n_lead,
@@ -440,7 +452,7 @@ int launch_sim_topk(const __half* k_hi, const __half* k_lo, const float* neg_s, 
   p.qpad = q_tiles * BQ;
   p.neg_s = neg_s; p.bsq = bsq;
   p.part_val = reinterpret_cast<float*>(workspace);
-  p.part_idx = reinterpret_cast<int*>(p.part_val + (size_t)kMaxSplit * kListCap * p.qpad);
+  p.part_idx = reinterpret_cast<int*>(p.part_val + (size_t)kMaxSplit * GROUPS * kListCap * p.qpad);
   static bool configured = false;
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(simtopk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -451,7 +463,7 @@ int launch_sim_topk(const __half* k_hi, const __half* k_lo, const float* neg_s, 
   simtopk_kernel<false><<<dim3(q_tiles, nsplit), THREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
   B200_LAUNCH_CHECK();
   merge_kernel<<<ceil_div(q, MERGE_WARPS), MERGE_WARPS * 32, 0, stream>>>(
-      p.part_val, p.part_idx, nsplit, top_k, q, p.qpad, out_idx, out_w, P, ldP, use_cnt, n_long, count_long,
+      p.part_val, p.part_idx, nsplit * GROUPS, top_k, q, p.qpad, out_idx, out_w, P, ldP, use_cnt, n_long, count_long,
       count_work);
   B200_LAUNCH_CHECK();
   if (life_cnt) {
