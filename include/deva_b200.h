@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DEVA_B200_ABI_VERSION 4
+#define DEVA_B200_ABI_VERSION 5
 #define DEVA_B200_LIST_PITCH 32 /* row pitch of top-k outputs == max supported top_k */
 #define DEVA_B200_MAX_GROUPS 256 /* objects per deva_b200_readout call */
 
@@ -101,6 +101,18 @@ DEVA_B200_API int deva_b200_readout(const void* values, int64_t values_ld, int64
 /* out_tok (optional; when non-NULL it replaces `out`): fp16 token-major result
  * out_tok[(object*q + j)*rows_per_group + r] with object = out_row[g] / rows_per_group - the layout the NHWC
  * decoder kernels consume. */
+
+/* Same read-out with the affinity operand generated on chip: instead of a dense [q, n_window] fp16 matrix the
+ * kernel takes the top-k lists written by deva_b200_sim_topk (idx/w: [q, 32]) and builds each 256-query x 64-slot
+ * affinity tile in shared memory (zeroed stage buffers + scatter of the ~top_k*256*64/n_window non-zeros), so the
+ * dense affinity never exists in HBM and only the value operand streams through TMA.
+ * workspace: deva_b200_readout_sparse_workspace_bytes(q, n_window) bytes (per-tile bucket offsets + entries). */
+DEVA_B200_API size_t deva_b200_readout_sparse_workspace_bytes(int q, int n_window);
+DEVA_B200_API int deva_b200_readout_sparse(const void* values, int64_t values_ld, int64_t values_rows,
+                                           const int32_t* val_row, const int32_t* out_row, int n_groups,
+                                           int rows_per_group, const int32_t* idx, const float* w, int top_k,
+                                           int n_window, int q, void* workspace, float* out, int64_t ld_out,
+                                           void* out_tok, deva_stream_t stream);
 
 /* ---- bank compaction (sieve_by_range / remove_obsolete_features, kv_memory_store.py:127-185) ----------
  * dst must not alias src.  idx: device int32 [n]. */

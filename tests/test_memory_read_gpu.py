@@ -69,7 +69,18 @@ def _read(nat, bank, qk, qe, k_obj, cv, top_k=30):
     out = torch.empty(k_obj * cv, q, device=dev)
     nat.readout(bank.values, bank.ld, k_obj * cv, [i * cv for i in range(k_obj)], [i * cv for i in range(k_obj)], cv,
                 P, ldp, bank.nw, q, out, q)
+    # fused variant: affinity tiles generated on chip from (idx, w) - must equal the dense-operand GEMM
+    out_sp = torch.empty_like(out)
+    rws = torch.empty(nat.readout_sparse_workspace_bytes(q, bank.nw), dtype=torch.uint8, device=dev)
+    nat.readout_sparse(bank.values, bank.ld, k_obj * cv, [i * cv for i in range(k_obj)], [i * cv for i in range(k_obj)],
+                       cv, idx, w, top_k, bank.nw, q, rws, out_sp, q)
+    tok = torch.empty(k_obj, q, cv, dtype=torch.float16, device=dev)
+    nat.readout_sparse(bank.values, bank.ld, k_obj * cv, [i * cv for i in range(k_obj)], [i * cv for i in range(k_obj)],
+                       cv, idx, w, top_k, bank.nw, q, rws, None, 0, out_tok=tok)
     torch.cuda.synchronize()
+    scale = max(1.0, float(out.abs().max()))
+    assert float((out_sp - out).abs().max()) < 1e-5 * scale, 'sparse-affinity readout differs from the dense-operand GEMM'
+    assert float((tok.float().permute(0, 2, 1).reshape(k_obj * cv, q) - out).abs().max()) < 2e-3 * scale
     return idx.cpu(), w.cpu(), P.float().cpu(), out.cpu(), (q_hi, q_lo, bsq)
 
 

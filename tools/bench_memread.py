@@ -45,8 +45,17 @@ def run(n, q, k_obj, iters=10, top_k=30):
     def stage_read():
         nat.readout(values, ld, rows, vr, vr, CV, P, ld, n, q, out, q)
 
+    rws = torch.empty(nat.readout_sparse_workspace_bytes(q, n), dtype=torch.uint8, device=dev)
+
+    def stage_topk_nodense():
+        nat.sim_topk(k_hi, k_lo, neg_s, n, 0, q_hi, q_lo, bsq, q, CK, top_k, ws, idx, w, None, 0, use, life, 0, False, True)
+
+    def stage_read_sparse():
+        nat.readout_sparse(values, ld, rows, vr, vr, CV, idx, w, top_k, n, q, rws, out, q)
+
     res = {}
-    for name, fn in (('pack_query', stage_pack), ('sim_topk', stage_topk), ('readout', stage_read)):
+    for name, fn in (('pack_query', stage_pack), ('sim_topk', stage_topk), ('readout', stage_read),
+                     ('sim_topk_lists_only', stage_topk_nodense), ('readout_fused', stage_read_sparse)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -59,9 +68,10 @@ def run(n, q, k_obj, iters=10, top_k=30):
         ts.sort()
         res[name] = ts[len(ts) // 2]
     flops = 2.0 * n * q * 2 * CK + 2.0 * rows * n * q
-    tot = res['sim_topk'] + res['readout']
+    tot = res['sim_topk_lists_only'] + res['readout_fused']
     res.update(n=n, q=q, k_obj=k_obj, gflop=flops / 1e9, fused_tflops=flops / tot / 1e9,
-               readout_tflops=2.0 * rows * n * q / res['readout'] / 1e9)
+               readout_tflops=2.0 * rows * n * q / res['readout'] / 1e9,
+               readout_fused_tflops=2.0 * rows * n * q / res['readout_fused'] / 1e9)
     return res
 
 

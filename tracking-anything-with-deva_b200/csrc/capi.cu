@@ -69,6 +69,17 @@ DEVA_B200_API int deva_b200_readout(const void* values, int64_t values_ld, int64
   return launch_readout(H(values), values_ld, values_rows, val_row, out_row, n_groups, rows_per_group, H(affinity),
                         ld_affinity, n_window, q, out, ld_out, H(out_tok), S(stream));
 }
+DEVA_B200_API size_t deva_b200_readout_sparse_workspace_bytes(int q, int n_window) {
+  return readout_sparse_workspace_bytes(q, n_window);
+}
+DEVA_B200_API int deva_b200_readout_sparse(const void* values, int64_t values_ld, int64_t values_rows,
+                                           const int32_t* val_row, const int32_t* out_row, int n_groups,
+                                           int rows_per_group, const int32_t* idx, const float* w, int top_k,
+                                           int n_window, int q, void* workspace, float* out, int64_t ld_out,
+                                           void* out_tok, deva_stream_t stream) {
+  return launch_readout_sparse(H(values), values_ld, values_rows, val_row, out_row, n_groups, rows_per_group, idx, w,
+                               top_k, n_window, q, workspace, out, ld_out, H(out_tok), S(stream));
+}
 DEVA_B200_API int deva_b200_gather_rows(void* dst, const void* src, const int32_t* idx, int n, int row_bytes, deva_stream_t stream) {
   return launch_gather_rows(dst, src, idx, n, row_bytes, S(stream));
 }

@@ -11,4 +11,12 @@ int launch_readout(const __half* values, long long values_ld, long long values_r
                    const int* out_row, int n_groups, int rows_per_group, const __half* P, long long ldP,
                    int n_window, int q, float* out, long long ldo, __half* out_tok, cudaStream_t stream);
 // out_tok (optional, replaces `out`): fp16 token-major [object, q, rows_per_group] with object = out_row / rows_per_group
+
+// Fused sparse-affinity variant: the B operand is generated in shared memory from the top-k lists
+// (idx/w: [q, 32] as written by launch_sim_topk), no dense affinity.  workspace: readout_sparse_workspace_bytes().
+size_t readout_sparse_workspace_bytes(int q, int n_window);
+int launch_readout_sparse(const __half* values, long long values_ld, long long values_rows, const int* val_row,
+                          const int* out_row, int n_groups, int rows_per_group, const int* idx, const float* w,
+                          int top_k, int n_window, int q, void* workspace, float* out, long long ldo, __half* out_tok,
+                          cudaStream_t stream);
 }  // namespace b200

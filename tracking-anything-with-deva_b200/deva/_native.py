@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libdeva_b200.so')
-ABI_VERSION = 4
+ABI_VERSION = 5
 LIST_PITCH = 32
 MAX_GROUPS = 256
 
@@ -50,6 +50,10 @@ _SIGNATURES = {
                                             c_void_p]),
     'deva_b200_readout': (c_int, [c_void_p, c_int64, c_int64, POINTER(c_int32), POINTER(c_int32), c_int, c_int,
                                   c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    'deva_b200_readout_sparse_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'deva_b200_readout_sparse': (c_int, [c_void_p, c_int64, c_int64, POINTER(c_int32), POINTER(c_int32), c_int, c_int,
+                                         c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                         c_void_p]),
     'deva_b200_gather_rows': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'deva_b200_gather_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'deva_b200_gather_cols_f16': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
@@ -166,6 +170,20 @@ def readout(values, values_ld, values_rows, val_row, out_row, rows_per_group, af
     _check(lib().deva_b200_readout(_ptr(values), values_ld, values_rows, arr_v, arr_o, n, rows_per_group,
                                    _ptr(affinity), ld_affinity, n_window, q, _ptr(out), ld_out, _ptr(out_tok),
                                    _stream()), 'readout')
+
+
+def readout_sparse_workspace_bytes(q, n_window):
+    return int(lib().deva_b200_readout_sparse_workspace_bytes(q, n_window))
+
+
+def readout_sparse(values, values_ld, values_rows, val_row, out_row, rows_per_group, idx, w, top_k, n_window, q,
+                   workspace, out, ld_out, out_tok=None):
+    n = len(val_row)
+    arr_v = (c_int32 * n)(*val_row)
+    arr_o = (c_int32 * n)(*out_row)
+    _check(lib().deva_b200_readout_sparse(_ptr(values), values_ld, values_rows, arr_v, arr_o, n, rows_per_group,
+                                          _ptr(idx), _ptr(w), top_k, n_window, q, _ptr(workspace), _ptr(out), ld_out,
+                                          _ptr(out_tok), _stream()), 'readout_sparse')
 
 
 def gather_rows(dst, src, idx, n, row_bytes):

@@ -134,20 +134,20 @@ class MemoryManager:
         wgt = self._buf('topk_w', (q, nat.LIST_PITCH), torch.float32, dev)
         for bank in self._banks.values():
             w0, lead, n_window = bank.window()
-            ldp = (n_window + 7) // 8 * 8
-            aff = self._buf('affinity', (q, ldp), torch.float16, dev)
             count_work = self.use_long_term
             count_long = self.use_long_term and self.count_long_term_usage and bank.long_size > 0
             nat.sim_topk(bank.k_hi[w0:], bank.k_lo[w0:], bank.neg_s[w0:], n_window, lead, q_hi, q_lo, bsq, q,
-                         self.CK, self.top_k, ws, idx, wgt, aff, ldp,
+                         self.CK, self.top_k, ws, idx, wgt, None, 0,
                          bank.use_cnt[w0:] if count_work else None, bank.life_cnt[w0:] if count_work else None,
                          bank.base - w0, count_long, count_work)
+            # readout GEMM with the affinity tiles generated on chip from the top-k lists (no dense [Q, N] matrix)
+            rws = self._buf('readout_ws', (nat.readout_sparse_workspace_bytes(q, n_window), ), torch.uint8, dev)
             objs = bank.objects
             for i in range(0, len(objs), nat.MAX_GROUPS):
                 part = objs[i:i + nat.MAX_GROUPS]
-                nat.readout(bank.values[:, :, w0:], bank.cap, bank.values.shape[0] * self.CV,
-                            [bank.slot_of[o] * self.CV for o in part], [order[o] * self.CV for o in part], self.CV,
-                            aff, ldp, n_window, q, out, q, out_tok)
+                nat.readout_sparse(bank.values[:, :, w0:], bank.cap, bank.values.shape[0] * self.CV,
+                                   [bank.slot_of[o] * self.CV for o in part], [order[o] * self.CV for o in part],
+                                   self.CV, idx, wgt, self.top_k, n_window, q, rws, out, q, out_tok)
         if self.read_events is not None:
             ev1 = torch.cuda.Event(enable_timing=True)
             ev1.record()
