@@ -19,6 +19,7 @@
 // Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..5 = epilogue.  Persistent CTAs, 4-stage
 //   smem ring, double-buffered accumulators.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "conv.h"
@@ -42,6 +43,9 @@ struct Params {
   int tiles_x, tiles_y, tw, th;
   int n_tiles, nt;
   int taps, cblocks;
+  int cs;        // cluster size: CTAs of a cluster work on `cs` consecutive pixel tiles of the SAME channel tile and
+                 // share the weight operand through TMA multicast (each CTA fetches 1/cs of it)
+  int m_tiles;   // batch * tiles_y * tiles_x
   signed char tap_map[kMaxTaps], tap_w[kMaxTaps], tap_dx[kMaxTaps], tap_dy[kMaxTaps];  // per k-entry: activation
                                                          // map, weight tap group, input offset
   const float* bias;
@@ -62,7 +66,8 @@ struct Params {
 
 struct Maps {
   CUtensorMap act[8];
-  CUtensorMap wgt;
+  CUtensorMap wgt;        // box {64, nt}
+  CUtensorMap wgt_slice;  // box {64, nt / cs} (cluster multicast)
 };
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, const int (&c)[5]) {
@@ -94,9 +99,14 @@ __device__ __forceinline__ void store_split(const float (&v)[32], __half* hi, __
   }
 }
 
-__device__ __forceinline__ void tile_decode(int tile, const Params& p, int& b, int& y0, int& x0, int& n0) {
-  const int nidx = tile % p.n_tiles;
-  int m = tile / p.n_tiles;
+// Work unit `u` of a cluster -> this CTA's tile.  Units enumerate (channel tile, group of cs pixel tiles); CTA `rank`
+// of the cluster takes pixel tile mg*cs + rank.  A pixel tile index past the end ("phantom") is clamped so the CTA
+// still takes part in the shared weight pipeline, and flagged so its epilogue stores nothing.
+__device__ __forceinline__ bool tile_decode(int u, int rank, const Params& p, int& b, int& y0, int& x0, int& n0) {
+  const int nidx = u % p.n_tiles;
+  int m = (u / p.n_tiles) * p.cs + rank;
+  const bool real = m < p.m_tiles;
+  m = real ? m : p.m_tiles - 1;
   const int tx = m % p.tiles_x;
   m /= p.tiles_x;
   const int ty = m % p.tiles_y;
@@ -104,6 +114,7 @@ __device__ __forceinline__ void tile_decode(int tile, const Params& p, int& b, i
   y0 = ty * p.th;
   x0 = tx * p.tw;
   n0 = nidx * p.nt;
+  return real;
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -124,20 +135,26 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.batch * p.tiles_y * p.tiles_x * p.n_tiles;
+  const int cs = p.cs;
+  const int rank = (cs > 1) ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
+  const int total_units = ((p.m_tiles + cs - 1) / cs) * p.n_tiles;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
   const int k_iters = p.taps * p.cblocks;
   const uint32_t stage_tx = A_BYTES + p.nt * BK * 2;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 8; ++i) tma_prefetch_desc(&maps.act[i]);
     tma_prefetch_desc(&maps.wgt);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    tma_prefetch_desc(&maps.wgt_slice);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], cs); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -145,9 +162,10 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int slice_rows = p.nt / cs;
+      for (int u = cluster_id; u < total_units; u += n_clusters) {
         int b, y0, x0, n0;
-        tile_decode(tile, p, b, y0, x0, n0);
+        tile_decode(u, rank, p, b, y0, x0, n0);
         for (int t = 0; t < p.taps; ++t) {
           int c[5] = {0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b, 0};  // (channel, x, y, image, 1)
           const CUtensorMap* am = &maps.act[p.tap_map[t]];
@@ -156,7 +174,12 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
             mbar_expect_tx(&full[stage], stage_tx);
             c[0] = cb * BK;
             tma_load_5d(sA + stage * A_BYTES, am, &full[stage], c);
-            tma_load_2d(sB + stage * B_BYTES_MAX, &maps.wgt, &full[stage], (p.tap_w[t] * p.cblocks + cb) * BK, n0);
+            if (cs == 1) {
+              tma_load_2d(sB + stage * B_BYTES_MAX, &maps.wgt, &full[stage], (p.tap_w[t] * p.cblocks + cb) * BK, n0);
+            } else {  // this CTA fetches rows [rank*slice, +slice) of the weight tile for the whole cluster
+              tma_load_2d_mcast(sB + stage * B_BYTES_MAX + rank * slice_rows * 128, &maps.wgt_slice, &full[stage],
+                                (p.tap_w[t] * p.cblocks + cb) * BK, n0 + rank * slice_rows, cmask);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -168,7 +191,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int u = cluster_id; u < total_units; u += n_clusters, ++it) {
         const int acc = it & 1;
         mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -182,7 +205,8 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
           for (int k = 0; k < BK / 16; ++k)
             umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
                      (ki | k) != 0);
-          umma_commit(&empty[stage]);
+          if (cs == 1) umma_commit(&empty[stage]);
+          else umma_commit_mcast(&empty[stage], cmask);  // the stage is free once EVERY CTA of the cluster has read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&acc_full[acc]);
@@ -201,11 +225,11 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       named_bar_sync(1, 128);
     }
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int u = cluster_id; u < total_units; u += n_clusters, ++it) {
       int b, y0, x0, n0;
-      tile_decode(tile, p, b, y0, x0, n0);
+      const bool real = tile_decode(u, rank, p, b, y0, x0, n0);
       const int y = y0 + ty, x = x0 + tx;
-      const bool live = (y < p.ho) && (x < p.wo);
+      const bool live = real && (y < p.ho) && (x < p.wo);
       const long long pix = ((long long)b * p.ho + y) * p.wo + x;
       const long long off = pix * p.cout + n0;
       const __half* res = p.res ? p.res + (p.res_batch_stride ? off : ((long long)y * p.wo + x) * p.cout + n0)
@@ -352,6 +376,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
 
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();  // nobody leaves while a peer may still multicast into this CTA
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -436,6 +461,7 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   p.tiles_x = ceil_div(wo, d.tw); p.tiles_y = ceil_div(ho, d.th);
   p.nt = d.nt; p.n_tiles = d.cout_pad / d.nt;
   p.cblocks = d.cin_pad / 64;
+  p.m_tiles = p.batch * p.tiles_y * p.tiles_x;
   p.bias = d.bias;
   p.res = reinterpret_cast<const __half*>(d.res);
   p.res_lo = reinterpret_cast<const __half*>(d.res_lo);
@@ -456,9 +482,57 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
     B200_CUDA(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  const long long total = (long long)p.batch * p.tiles_y * p.tiles_x * p.n_tiles;
-  const int grid = (int)(total < sm_count() ? total : sm_count());
-  conv_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(maps, p);
+  // Cluster size: share the weight tile across 4 (or 2) CTAs when there is enough work to keep every SM busy.
+  static const int max_cs = [] { const char* e = getenv("DEVA_B200_CONV_CLUSTER"); return e ? atoi(e) : 2; }();
+  int cs = 1;
+  for (int c = max_cs; c >= 2; c >>= 1)
+    if ((c == 2 || c == 4) && (d.nt / c) % 8 == 0 && (long long)p.m_tiles * p.n_tiles >= 2ll * sm_count() && sm_count() % c == 0) {
+      cs = c;
+      break;
+    }
+  p.cs = cs;
+  if (cs > 1 && make_tmap_2d(&maps.wgt_slice, TmapType::F16, d.w_packed, (uint64_t)w_groups * ktaps * d.cin_pad,
+                             d.cout_pad, (uint64_t)w_groups * ktaps * d.cin_pad * 2, 64, d.nt / cs, &err)) {
+    set_error("conv: %s", err ? err : "weight slice tensor map");
+    return 3;
+  }
+  if (cs == 1) maps.wgt_slice = maps.wgt;
+  const long long units = (long long)((p.m_tiles + cs - 1) / cs) * p.n_tiles;
+  // co-resident clusters (a GPC with a leftover odd SM count strands SMs for cs = 4): ask the runtime once
+  static int max_clusters[5] = {0, 0, 0, 0, 0};
+  if (cs > 1 && max_clusters[cs] == 0) {
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3(sm_count() / cs * cs);
+    q.blockDim = dim3(THREADS);
+    q.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute a[1];
+    a[0].id = cudaLaunchAttributeClusterDimension;
+    a[0].val.clusterDim.x = cs; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
+    q.attrs = a; q.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_kernel, &q) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = sm_count() / cs; }
+    max_clusters[cs] = n;
+  }
+  long long clusters = cs > 1 ? max_clusters[cs] : sm_count();
+  if (units < clusters) clusters = units;
+  const int grid = (int)(clusters * cs);
+  if (cs == 1) {
+    conv_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(maps, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel, maps, p));
+  }
   B200_LAUNCH_CHECK();
   return 0;
 }
