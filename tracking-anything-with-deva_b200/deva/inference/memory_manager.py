@@ -52,6 +52,7 @@ class MemoryManager:
         self.read_events = None
         # 'nhwc': match_memory returns fp16 token-major-backed views (what the native NHWC decoder consumes)
         self.readout_layout = 'nchw'
+        self.fused_min_work = 16_000_000  # n_window * q above which the fused sparse-affinity readout is used
 
     def _read_long_term_config(self, config: Dict) -> None:
         self.max_mem_frames = config['max_mid_term_frames']
@@ -136,18 +137,30 @@ class MemoryManager:
             w0, lead, n_window = bank.window()
             count_work = self.use_long_term
             count_long = self.use_long_term and self.count_long_term_usage and bank.long_size > 0
+            # large reads: affinity tiles are generated on chip by the readout kernel; small reads (where its fixed
+            # costs dominate): dense fp16 affinity + plain GEMM
+            fused = n_window * q >= self.fused_min_work
+            aff, ldp = None, 0
+            if not fused:
+                ldp = (n_window + 7) // 8 * 8
+                aff = self._buf('affinity', (q, ldp), torch.float16, dev)
             nat.sim_topk(bank.k_hi[w0:], bank.k_lo[w0:], bank.neg_s[w0:], n_window, lead, q_hi, q_lo, bsq, q,
-                         self.CK, self.top_k, ws, idx, wgt, None, 0,
+                         self.CK, self.top_k, ws, idx, wgt, aff, ldp,
                          bank.use_cnt[w0:] if count_work else None, bank.life_cnt[w0:] if count_work else None,
                          bank.base - w0, count_long, count_work)
-            # readout GEMM with the affinity tiles generated on chip from the top-k lists (no dense [Q, N] matrix)
-            rws = self._buf('readout_ws', (nat.readout_sparse_workspace_bytes(q, n_window), ), torch.uint8, dev)
             objs = bank.objects
+            if fused:
+                rws = self._buf('readout_ws', (nat.readout_sparse_workspace_bytes(q, n_window), ), torch.uint8, dev)
             for i in range(0, len(objs), nat.MAX_GROUPS):
                 part = objs[i:i + nat.MAX_GROUPS]
-                nat.readout_sparse(bank.values[:, :, w0:], bank.cap, bank.values.shape[0] * self.CV,
-                                   [bank.slot_of[o] * self.CV for o in part], [order[o] * self.CV for o in part],
-                                   self.CV, idx, wgt, self.top_k, n_window, q, rws, out, q, out_tok)
+                rows_v = [bank.slot_of[o] * self.CV for o in part]
+                rows_o = [order[o] * self.CV for o in part]
+                if fused:
+                    nat.readout_sparse(bank.values[:, :, w0:], bank.cap, bank.values.shape[0] * self.CV, rows_v, rows_o,
+                                       self.CV, idx, wgt, self.top_k, n_window, q, rws, out, q, out_tok)
+                else:
+                    nat.readout(bank.values[:, :, w0:], bank.cap, bank.values.shape[0] * self.CV, rows_v, rows_o,
+                                self.CV, aff, ldp, n_window, q, out, q, out_tok)
         if self.read_events is not None:
             ev1 = torch.cuda.Event(enable_timing=True)
             ev1.record()
