@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DEVA_B200_ABI_VERSION 5
+#define DEVA_B200_ABI_VERSION 6
 #define DEVA_B200_LIST_PITCH 32 /* row pitch of top-k outputs == max supported top_k */
 #define DEVA_B200_MAX_GROUPS 256 /* objects per deva_b200_readout call */
 
@@ -82,8 +82,18 @@ DEVA_B200_API size_t deva_b200_simtopk_workspace_bytes(int q);
 DEVA_B200_API int deva_b200_sim_topk(const void* k_hi, const void* k_lo, const float* neg_s, int n_window, int n_lead,
                        const void* q_hi, const void* q_lo, const float* bsq, int q, int ck, int top_k,
                        void* workspace, int32_t* out_idx, float* out_w, void* affinity, int64_t ld_affinity,
-                       float* use_cnt, float* life_cnt, int n_long, int count_long, int count_work,
+                       float* use_cnt, float* life_cnt, int n_long, int count_long, int count_work, float* out_sim,
                        deva_stream_t stream);
+/* out_sim (optional): fp32 [q, 32] raw similarities of the selected slots (descending; -inf beyond top_k) - what a
+ * bank-sharded read exchanges between ranks.
+ *
+ * deva_b200_merge_lists: global top-k + softmax over n_lists (<= 16) candidate lists per query, layout
+ * part_val/part_idx [n_lists][32][q_pitch] (query index fastest; idx < 0 = empty entry).  It is the cross-rank merge of a
+ * memory bank sharded along the slot axis: every rank all-gathers the (similarity, global slot) lists
+ * of all ranks and obtains the identical global top-k set and softmax weights. */
+DEVA_B200_API int deva_b200_merge_lists(const float* part_val, const int32_t* part_idx, int n_lists, int top_k, int q,
+                                        int q_pitch, int32_t* out_idx, float* out_w, float* out_sim,
+                                        deva_stream_t stream);
 /* get_similarity + do_softmax without top-k (max-subtracted branch, memory_utils.py:66-71) as used by
  * MemoryManager.consolidation (memory_manager.py:262-273).  sim_ws: [q, ld_sim] fp32 scratch;
  * affinity: [q, ld_affinity] fp16;  shr_out[q] = sum_n affinity[q,n]*shrinkage[n] (optional). */

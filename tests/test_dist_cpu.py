@@ -52,3 +52,20 @@ def test_round_robin_assignment():
     from deva.utils.dist_utils import assign_clips
     assert assign_clips(64, 8, 3) == list(range(3, 64, 8))
     assert sum(len(assign_clips(10, 4, r)) for r in range(4)) == 10
+
+
+def test_shard_bounds_and_localise():
+    from deva.inference.sharded_memory import localise, shard_bounds
+    n, world = 50000, 8
+    cover = [shard_bounds(n, world, r) for r in range(world)]
+    assert cover[0][0] == 0 and cover[-1][1] == n
+    assert all(cover[i][1] == cover[i + 1][0] for i in range(world - 1))
+    assert all(lo % 8 == 0 for lo, _ in cover)
+    assert shard_bounds(10, 4, 3) == (10, 10)  # empty trailing shard
+    idx = torch.tensor([[3, 17, 40, 9]], dtype=torch.int32)
+    w = torch.tensor([[0.4, 0.3, 0.2, 0.1]])
+    li, lw = localise(idx, w, 8, 24)
+    assert li.tolist() == [[0, 9, 0, 1]] and lw.tolist() == [[0.0, 0.30000001192092896, 0.0, 0.10000000149011612]]
+    # weights of all shards add back up to the global list
+    tot = sum(localise(idx, w, *shard_bounds(48, 3, r))[1] for r in range(3))
+    assert torch.allclose(tot, w)

@@ -292,9 +292,9 @@ constexpr int MERGE_WARPS = 8;
 __global__ void __launch_bounds__(MERGE_WARPS * 32)
 merge_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int nsplit, int top_k, int q,
              int qpad, int* __restrict__ out_idx, float* __restrict__ out_w, __half* __restrict__ P, long long ldP,
-             float* __restrict__ use_cnt, int n_long, int add_long, int add_work) {
-  __shared__ float cv[MERGE_WARPS][kMaxSplit * GROUPS * kListCap];
-  __shared__ int ci[MERGE_WARPS][kMaxSplit * GROUPS * kListCap];
+             float* __restrict__ use_cnt, int n_long, int add_long, int add_work, float* __restrict__ out_sim) {
+  __shared__ float cv[MERGE_WARPS][kMaxSplit * GROUPS * kListCap + 1];  // +1: rows land in different banks
+  __shared__ int ci[MERGE_WARPS][kMaxSplit * GROUPS * kListCap + 1];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x * MERGE_WARPS;
   const int C = nsplit * top_k;
@@ -339,6 +339,7 @@ merge_kernel(const float* __restrict__ part_val, const int* __restrict__ part_id
   const float wgt = e / sum;
   out_idx[(long long)qi * kListCap + lane] = (lane < top_k) ? sel_i : 0;
   out_w[(long long)qi * kListCap + lane] = (lane < top_k) ? wgt : 0.f;
+  if (out_sim) out_sim[(long long)qi * kListCap + lane] = (lane < top_k) ? sel_v : -CUDART_INF_F;
   if (lane < top_k) {
     if (P) P[(long long)qi * ldP + sel_i] = __float2half_rn(wgt);
     if (use_cnt && ((sel_i < n_long) ? add_long : add_work)) atomicAdd(use_cnt + sel_i, wgt);
@@ -433,7 +434,7 @@ size_t simtopk_workspace_bytes(int q) {
 int launch_sim_topk(const __half* k_hi, const __half* k_lo, const float* neg_s, int n_window, int n_lead,
                     const __half* q_hi, const __half* q_lo, const float* bsq, int q, int ck, int top_k,
                     void* workspace, int* out_idx, float* out_w, __half* P, long long ldP, float* use_cnt,
-                    float* life_cnt, int n_long, int count_long, int count_work, cudaStream_t stream) {
+                    float* life_cnt, int n_long, int count_long, int count_work, float* out_sim, cudaStream_t stream) {
   using namespace simtopk;
   B200_REQUIRE(ck == 32 || ck == 64, "simtopk: key_dim %d unsupported (32 or 64)", ck);
   B200_REQUIRE(top_k >= 1 && top_k <= kListCap, "simtopk: top_k %d out of range [1,%d]", top_k, kListCap);
@@ -464,7 +465,7 @@ int launch_sim_topk(const __half* k_hi, const __half* k_lo, const float* neg_s, 
   B200_LAUNCH_CHECK();
   merge_kernel<<<ceil_div(q, MERGE_WARPS), MERGE_WARPS * 32, 0, stream>>>(
       p.part_val, p.part_idx, nsplit * GROUPS, top_k, q, p.qpad, out_idx, out_w, P, ldP, use_cnt, n_long, count_long,
-      count_work);
+      count_work, out_sim);
   B200_LAUNCH_CHECK();
   if (life_cnt) {
     // life += 1 for every slot whose usage is being counted (kv_memory_store.py:118-125)
@@ -475,6 +476,19 @@ int launch_sim_topk(const __half* k_hi, const __half* k_lo, const float* neg_s, 
       B200_LAUNCH_CHECK();
     }
   }
+  return 0;
+}
+
+// Global top-k + softmax over `n_lists` candidate lists per query (layout [n_lists][kListCap][qpad], entries with
+// idx < 0 are empty): the cross-rank merge of a bank-sharded read, and the second stage of launch_sim_topk.
+int launch_merge_lists(const float* part_val, const int* part_idx, int n_lists, int top_k, int q, int qpad, int* out_idx,
+                       float* out_w, float* out_sim, cudaStream_t stream) {
+  using namespace simtopk;
+  B200_REQUIRE(n_lists >= 1 && n_lists <= kMaxSplit * GROUPS, "merge: n_lists %d out of range [1,%d]", n_lists, kMaxSplit * GROUPS);
+  B200_REQUIRE(top_k >= 1 && top_k <= kListCap && q >= 1 && qpad >= q, "merge: bad shape");
+  merge_kernel<<<ceil_div(q, MERGE_WARPS), MERGE_WARPS * 32, 0, stream>>>(part_val, part_idx, n_lists, top_k, q, qpad, out_idx,
+                                                                         out_w, nullptr, 0, nullptr, 0, 0, 0, out_sim);
+  B200_LAUNCH_CHECK();
   return 0;
 }
 

@@ -18,7 +18,12 @@ size_t simtopk_workspace_bytes(int q);
 int launch_sim_topk(const __half* k_hi, const __half* k_lo, const float* neg_s, int n_window, int n_lead,
                     const __half* q_hi, const __half* q_lo, const float* bsq, int q, int ck, int top_k,
                     void* workspace, int* out_idx, float* out_w, __half* P, long long ldP, float* use_cnt,
-                    float* life_cnt, int n_long, int count_long, int count_work, cudaStream_t stream);
+                    float* life_cnt, int n_long, int count_long, int count_work, float* out_sim, cudaStream_t stream);
+// out_sim (optional): [q, kListCap] raw similarities of the selected slots (descending), -inf beyond top_k
+
+constexpr int kMaxMergeLists = 16;
+int launch_merge_lists(const float* part_val, const int* part_idx, int n_lists, int top_k, int q, int qpad, int* out_idx,
+                       float* out_w, float* out_sim, cudaStream_t stream);
 
 // Full-softmax variant (consolidation): sim_ws [q, ld_sim] fp32 scratch, P [q, ldP] fp16,
 // shr_out[q] = sum_n P[q,n] * shr[n] (optional).
