@@ -15,9 +15,9 @@ CK, CV = 64, 512
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--n', type=int, default=50000)
-    ap.add_argument('--q', type=int, default=8160)
-    ap.add_argument('--k', type=int, default=32)
+    ap.add_argument('--slots', dest='n', type=int, default=50000)
+    ap.add_argument('--queries', dest='q', type=int, default=8160)
+    ap.add_argument('--objects', dest='k', type=int, default=32)
     ap.add_argument('--check', action='store_true', help='compare with the unsharded read on rank 0 (needs the memory)')
     ap.add_argument('--iters', type=int, default=10)
     a = ap.parse_args()

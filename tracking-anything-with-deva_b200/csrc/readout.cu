@@ -217,7 +217,8 @@ bucket_kernel(const int* __restrict__ idx, const float* __restrict__ w, int q, i
   const int total = nq * top_k;
   for (int i = threadIdx.x; i < total; i += 256) {
     const int ql = i / top_k, j = i - ql * top_k;
-    atomicAdd(&hist[idx[(long long)(q0 + ql) * kListCapR + j] / BK + 1], 1);
+    const long long e = (long long)(q0 + ql) * kListCapR + j;
+    if (w[e] != 0.f) atomicAdd(&hist[idx[e] / BK + 1], 1);  // zero-weight entries (padding, other shards' slots) are dropped
   }
   __syncthreads();
   if (threadIdx.x == 0) {  // k_blocks is small (N/64): serial scan is fine
@@ -227,6 +228,7 @@ bucket_kernel(const int* __restrict__ idx, const float* __restrict__ w, int q, i
   __syncthreads();
   for (int i = threadIdx.x; i < total; i += 256) {
     const int ql = i / top_k, j = i - ql * top_k;
+    if (w[(long long)(q0 + ql) * kListCapR + j] == 0.f) continue;
     const int n = idx[(long long)(q0 + ql) * kListCapR + j];
     const int kb = n / BK;
     const int pos = atomicAdd(&hist[kb], 1);
