@@ -189,3 +189,52 @@ def test_dense_softmax_matches_oracle():
     aff = mm.dense_affinity(sim, None)
     assert float((P.float().cpu()[:, 2:2 + n] - aff.t()).abs().max()) < 6e-4
     assert float((shr_out.cpu() - (ms.reshape(1, -1) @ aff).reshape(-1)).abs().max()) < 1e-4
+
+
+def test_sharded_reader_single_rank_matches_oracle():
+    """ShardedBankReader (world 1): local top-k -> list merge -> localise -> sparse readout with zero-weight padding."""
+    nat = _native()
+    from deva.inference.sharded_memory import ShardedBankReader, localise, shard_bounds
+    n, q, k_obj, cv = 3000, 500, 2, 128
+    mk, ms, qk, qe, mv = _make(n, q, k_obj, cv, 77)
+    rd = ShardedBankReader(CK, cv, k_obj, n, 0, 'cuda')
+    rd.load(mk.cuda(), ms.cuda(), mv.cuda())
+    out = rd.read(qk.cuda(), qe.cuda()).cpu()
+    sim = mm.similarity(mk.double(), ms.double(), qk.double(), qe.double())
+    ref = mm.readout(mm.dense_affinity(sim, 30), mv.double()).float()
+    assert float((out - ref).abs().max()) < 4e-3 * max(1.0, float(ref.abs().max()))
+    assert float((rd.use_cnt.cpu() - mm.dense_affinity(sim, 30).sum(1).float()).abs().max()) < 1e-3
+    # emulate 3 shards on one device: per-shard partial readouts must add up to the full one
+    total = torch.zeros_like(out)
+    lists_v, lists_i = [], []
+    shards = [shard_bounds(n, 3, r) for r in range(3)]
+    readers = []
+    for lo, hi in shards:
+        r = ShardedBankReader(CK, cv, k_obj, hi - lo, lo, 'cuda')
+        r.load(mk[:, lo:hi].cuda(), ms[lo:hi].cuda(), mv[:, lo:hi].cuda())
+        readers.append(r)
+    # run the protocol by hand (no process group): gather the local lists, merge, localise, read
+    qk_d, qe_d = qk.cuda(), qe.cuda()
+    q_hi = torch.empty(q, 2 * CK, dtype=torch.float16, device='cuda'); q_lo = torch.empty_like(q_hi)
+    bsq = torch.empty(q, device='cuda')
+    nat.pack_query(qk_d.contiguous(), qe_d.contiguous(), q, 1, CK, q, q_hi, q_lo, bsq)
+    for r in readers:
+        idx = torch.empty(q, 32, dtype=torch.int32, device='cuda'); w = torch.empty(q, 32, device='cuda')
+        s_ = torch.empty(q, 32, device='cuda')
+        ws = torch.empty(nat.simtopk_workspace_bytes(q), dtype=torch.uint8, device='cuda')
+        nat.sim_topk(r.k_hi, r.k_lo, r.neg_s, r.n, 0, q_hi, q_lo, bsq, q, CK, 30, ws, idx, w, None, 0, None, None, 0,
+                     False, False, out_sim=s_)
+        valid = torch.arange(32, device='cuda').view(1, -1) < 30
+        lists_v.append(s_.t().contiguous())
+        lists_i.append(torch.where(valid, idx + r.offset, torch.full_like(idx, -1)).t().contiguous())
+    g_sel = torch.empty(q, 32, dtype=torch.int32, device='cuda'); g_w = torch.empty(q, 32, device='cuda')
+    nat.merge_lists(torch.stack(lists_v), torch.stack(lists_i), 3, 30, q, q, g_sel, g_w)
+    for r in readers:
+        il, wl = localise(g_sel, g_w, r.offset, r.offset + r.n)
+        part = torch.zeros(k_obj * cv, q, device='cuda')
+        rws = torch.empty(nat.readout_sparse_workspace_bytes(q, r.n), dtype=torch.uint8, device='cuda')
+        rows = [i * cv for i in range(k_obj)]
+        nat.readout_sparse(r.values, r.ld, k_obj * cv, rows, rows, cv, il, wl, 32, r.n, q, rws, part, q)
+        total += part.cpu()
+    torch.cuda.synchronize()
+    assert float((total - out).abs().max()) < 1e-5 * max(1.0, float(out.abs().max()))
