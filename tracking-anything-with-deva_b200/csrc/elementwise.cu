@@ -43,23 +43,35 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ src, float* __res
 // im2col for the 7x7 stride-2 pad-3 stems (resnet.py:120): planes fp32 [B, C, H, W] -> fp16 [B, H/2, W/2, Kp]
 // with column k = (kh*7 + kw)*C + c for k < 49*C and zeros up to Kp (a multiple of 64).  The stem then runs
 // as a 1x1 implicit GEMM over Kp "channels" on the tensor cores.
+constexpr int IM_XT = 64;  // output columns per block
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const float* __restrict__ src, __half* __restrict__ dst, __half* __restrict__ dst_lo,
                    int B, int C, int H, int W, int Kp) {
-  // blockIdx.y = (image, output row); threads sweep (output column, k) with k fastest -> coalesced stores
+  // Block = (image b, output row yo, IM_XT output columns).  The 7 input rows x (2*IM_XT + 5) input columns of all C
+  // planes are staged in shared memory with coalesced loads; the columns are then written k-fastest (coalesced).
+  extern __shared__ float patch[];  // [C][7][PW]
   const int Ho = H / 2, Wo = W / 2;
+  const int PW = 2 * IM_XT + 5;
   const int b = blockIdx.y / Ho, yo = blockIdx.y - b * Ho;
-  const int row_elems = Wo * Kp;
+  const int xo0 = blockIdx.x * IM_XT;
+  const int x_in0 = 2 * xo0 - 3, y_in0 = 2 * yo - 3;
   const float* img = src + (long long)b * C * H * W;
-  const long long out_base = ((long long)b * Ho + yo) * (long long)row_elems;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < row_elems; i += gridDim.x * 256) {
-    const int xo = i / Kp, k = i - xo * Kp;
+  for (int i = threadIdx.x; i < C * 7 * PW; i += 256) {
+    const int px = i % PW, r = (i / PW) % 7, c = i / (7 * PW);
+    const int y = y_in0 + r, x = x_in0 + px;
+    patch[i] = (y >= 0 && y < H && x >= 0 && x < W) ? img[((long long)c * H + y) * W + x] : 0.f;
+  }
+  __syncthreads();
+  const int nx = min(IM_XT, Wo - xo0);
+  const long long out_base = (((long long)b * Ho + yo) * Wo + xo0) * Kp;
+  const int kreal = 49 * C;
+  for (int i = threadIdx.x; i < nx * Kp; i += 256) {
+    const int xl = i / Kp, k = i - xl * Kp;
     float v = 0.f;
-    if (k < 49 * C) {
+    if (k < kreal) {
       const int tap = k / C, c = k - tap * C;
       const int ky = tap / 7, kx = tap - ky * 7;
-      const int y = 2 * yo + ky - 3, x = 2 * xo + kx - 3;
-      if (y >= 0 && y < H && x >= 0 && x < W) v = img[((long long)c * H + y) * W + x];
+      v = patch[(c * 7 + ky) * PW + 2 * xl + kx];
     }
     const __half hv = __float2half_rn(v);
     dst[out_base + i] = hv;
@@ -448,8 +460,9 @@ int ew_nhwc_to_nchw(const __half* src, float* dst, int B, int C, int H, int W, c
 }
 int ew_stem_im2col(const float* src, __half* dst, __half* dst_lo, int B, int C, int H, int W, int Kp, cudaStream_t s) {
   B200_REQUIRE(H % 2 == 0 && W % 2 == 0 && Kp % 64 == 0 && Kp >= 49 * C, "stem_im2col: bad shape");
-  const int row_elems = (W / 2) * Kp;
-  ew::stem_im2col_kernel<<<dim3(ceil_div(row_elems, 256 * 4), B * (H / 2)), 256, 0, s>>>(src, dst, dst_lo, B, C, H, W, Kp);
+  B200_REQUIRE(C >= 1 && C <= 8, "stem_im2col: at most 8 input planes");
+  const size_t smem = (size_t)C * 7 * (2 * ew::IM_XT + 5) * sizeof(float);
+  ew::stem_im2col_kernel<<<dim3(ceil_div(W / 2, ew::IM_XT), B * (H / 2)), 256, smem, s>>>(src, dst, dst_lo, B, C, H, W, Kp);
   B200_LAUNCH_CHECK();
   return 0;
 }
