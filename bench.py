@@ -238,7 +238,7 @@ def run_ours(args):
         achieved = flops / (read_ms * 1e-3) / 1e12
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get(args.workload)
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get(args.workload)  # readout_sparse_kernel
         except Exception:
             pass
         h2d = int(clip.frames_host[0].numel() * 4)
@@ -253,7 +253,8 @@ def run_ours(args):
                        'parallelism': f'clip-parallel x{world}' if world > 1 else 'single clip',
                        'l2': 'per-step working set (activations > 2 GB) exceeds the 126 MB L2; no explicit flush',
                        'weights': 'synthetic_state_dict(seed=0), real architecture (69.2 M parameters)'},
-            'roofline': {'kernel': 'fused affinity path: pack_query + sim_topk(tcgen05 fp16x3) + merge + readout(tcgen05)',
+            'roofline': {'kernel': 'fused affinity path: pack_query + sim_topk(tcgen05 fp16x3) + merge + bucket + readout_sparse(tcgen05, '
+                                   'affinity tiles built in smem); traffic = DRAM bytes of readout_sparse_kernel (ncu)',
                          'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'ms_per_launch': read_ms, 'flops_per_launch': flops},

@@ -44,38 +44,43 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ src, float* __res
 // with column k = (kh*7 + kw)*C + c for k < 49*C and zeros up to Kp (a multiple of 64).  The stem then runs
 // as a 1x1 implicit GEMM over Kp "channels" on the tensor cores.
 constexpr int IM_XT = 64;  // output columns per block
+constexpr int IM_YT = 4;   // output rows per block
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const float* __restrict__ src, __half* __restrict__ dst, __half* __restrict__ dst_lo,
                    int B, int C, int H, int W, int Kp) {
-  // Block = (image b, output row yo, IM_XT output columns).  The 7 input rows x (2*IM_XT + 5) input columns of all C
-  // planes are staged in shared memory with coalesced loads; the columns are then written k-fastest (coalesced).
-  extern __shared__ float patch[];  // [C][7][PW]
+  // Block = (image b, IM_YT output rows, IM_XT output columns).  The (2*IM_YT + 5) input rows x (2*IM_XT + 5) input
+  // columns of all C planes are staged in shared memory with coalesced loads; the im2col rows are then written
+  // k-fastest (coalesced 2-byte stores, 128+ contiguous bytes per output pixel).
+  extern __shared__ float patch[];  // [C][PH][PW]
   const int Ho = H / 2, Wo = W / 2;
-  const int PW = 2 * IM_XT + 5;
-  const int b = blockIdx.y / Ho, yo = blockIdx.y - b * Ho;
+  constexpr int PW = 2 * IM_XT + 5, PH = 2 * IM_YT + 5;
+  const int ytiles = (Ho + IM_YT - 1) / IM_YT;
+  const int b = blockIdx.y / ytiles, yo0 = (blockIdx.y - b * ytiles) * IM_YT;
   const int xo0 = blockIdx.x * IM_XT;
-  const int x_in0 = 2 * xo0 - 3, y_in0 = 2 * yo - 3;
+  const int x_in0 = 2 * xo0 - 3, y_in0 = 2 * yo0 - 3;
   const float* img = src + (long long)b * C * H * W;
-  for (int i = threadIdx.x; i < C * 7 * PW; i += 256) {
-    const int px = i % PW, r = (i / PW) % 7, c = i / (7 * PW);
+  for (int i = threadIdx.x; i < C * PH * PW; i += 256) {
+    const int px = i % PW, r = (i / PW) % PH, c = i / (PH * PW);
     const int y = y_in0 + r, x = x_in0 + px;
     patch[i] = (y >= 0 && y < H && x >= 0 && x < W) ? img[((long long)c * H + y) * W + x] : 0.f;
   }
   __syncthreads();
-  const int nx = min(IM_XT, Wo - xo0);
-  const long long out_base = (((long long)b * Ho + yo) * Wo + xo0) * Kp;
+  const int nx = min(IM_XT, Wo - xo0), ny = min(IM_YT, Ho - yo0);
   const int kreal = 49 * C;
-  for (int i = threadIdx.x; i < nx * Kp; i += 256) {
-    const int xl = i / Kp, k = i - xl * Kp;
+  const int per_row = nx * Kp;
+  for (int i = threadIdx.x; i < ny * per_row; i += 256) {
+    const int yl = i / per_row, rem = i - yl * per_row;
+    const int xl = rem / Kp, k = rem - xl * Kp;
     float v = 0.f;
     if (k < kreal) {
       const int tap = k / C, c = k - tap * C;
       const int ky = tap / 7, kx = tap - ky * 7;
-      v = patch[(c * 7 + ky) * PW + 2 * xl + kx];
+      v = patch[(c * PH + 2 * yl + ky) * PW + 2 * xl + kx];
     }
+    const long long o = (((long long)b * Ho + yo0 + yl) * Wo + xo0) * Kp + rem;
     const __half hv = __float2half_rn(v);
-    dst[out_base + i] = hv;
-    if (dst_lo) dst_lo[out_base + i] = __float2half_rn(v - __half2float(hv));
+    dst[o] = hv;
+    if (dst_lo) dst_lo[o] = __float2half_rn(v - __half2float(hv));
   }
 }
 
@@ -461,8 +466,8 @@ int ew_nhwc_to_nchw(const __half* src, float* dst, int B, int C, int H, int W, c
 int ew_stem_im2col(const float* src, __half* dst, __half* dst_lo, int B, int C, int H, int W, int Kp, cudaStream_t s) {
   B200_REQUIRE(H % 2 == 0 && W % 2 == 0 && Kp % 64 == 0 && Kp >= 49 * C, "stem_im2col: bad shape");
   B200_REQUIRE(C >= 1 && C <= 8, "stem_im2col: at most 8 input planes");
-  const size_t smem = (size_t)C * 7 * (2 * ew::IM_XT + 5) * sizeof(float);
-  ew::stem_im2col_kernel<<<dim3(ceil_div(W / 2, ew::IM_XT), B * (H / 2)), 256, smem, s>>>(src, dst, dst_lo, B, C, H, W, Kp);
+  const size_t smem = (size_t)C * (2 * ew::IM_YT + 5) * (2 * ew::IM_XT + 5) * sizeof(float);
+  ew::stem_im2col_kernel<<<dim3(ceil_div(W / 2, ew::IM_XT), B * ceil_div(H / 2, ew::IM_YT)), 256, smem, s>>>(src, dst, dst_lo, B, C, H, W, Kp);
   B200_LAUNCH_CHECK();
   return 0;
 }
