@@ -14,6 +14,21 @@ namespace ew {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+__device__ __forceinline__ void ld8(const __half* p, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { const float2 t = __half22float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+}
+__device__ __forceinline__ void st8(__half* p, const float (&f)[8], bool relu) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    h[e] = relu ? __floats2half2_rn(fmaxf(f[2 * e], 0.f), fmaxf(f[2 * e + 1], 0.f)) : __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+
 // ---------------------------------------------------------------- layout conversion
 // fp32 NCHW [B,C,H,W] -> fp16 NHWC [B,H,W,Cp] (channels >= C are zero)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __half* __restrict__ dst, int B, int C, int H, int W,
@@ -44,62 +59,49 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ src, float* __res
 // with column k = (kh*7 + kw)*C + c for k < 49*C and zeros up to Kp (a multiple of 64).  The stem then runs
 // as a 1x1 implicit GEMM over Kp "channels" on the tensor cores.
 constexpr int IM_XT = 64;  // output columns per block
-constexpr int IM_YT = 4;   // output rows per block
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const float* __restrict__ src, __half* __restrict__ dst, __half* __restrict__ dst_lo,
                    int B, int C, int H, int W, int Kp) {
-  // Block = (image b, IM_YT output rows, IM_XT output columns).  The (2*IM_YT + 5) input rows x (2*IM_XT + 5) input
-  // columns of all C planes are staged in shared memory with coalesced loads; the im2col rows are then written
-  // k-fastest (coalesced 2-byte stores, 128+ contiguous bytes per output pixel).
-  extern __shared__ float patch[];  // [C][PH][PW]
+  // Block = (image b, output row yo, IM_XT output columns).  The 7 input rows x (2*IM_XT + 5) input columns of all C
+  // planes are staged in shared memory with coalesced loads; each thread then emits 8 consecutive im2col columns
+  // (one 16-byte store for the fp16 values, one for the remainders).
+  extern __shared__ float patch[];  // [C][7][PW]
   const int Ho = H / 2, Wo = W / 2;
-  constexpr int PW = 2 * IM_XT + 5, PH = 2 * IM_YT + 5;
-  const int ytiles = (Ho + IM_YT - 1) / IM_YT;
-  const int b = blockIdx.y / ytiles, yo0 = (blockIdx.y - b * ytiles) * IM_YT;
+  constexpr int PW = 2 * IM_XT + 5;
+  const int b = blockIdx.y / Ho, yo = blockIdx.y - b * Ho;
   const int xo0 = blockIdx.x * IM_XT;
-  const int x_in0 = 2 * xo0 - 3, y_in0 = 2 * yo0 - 3;
+  const int x_in0 = 2 * xo0 - 3, y_in0 = 2 * yo - 3;
   const float* img = src + (long long)b * C * H * W;
-  for (int i = threadIdx.x; i < C * PH * PW; i += 256) {
-    const int px = i % PW, r = (i / PW) % PH, c = i / (PH * PW);
+  for (int i = threadIdx.x; i < C * 7 * PW; i += 256) {
+    const int px = i % PW, r = (i / PW) % 7, c = i / (7 * PW);
     const int y = y_in0 + r, x = x_in0 + px;
     patch[i] = (y >= 0 && y < H && x >= 0 && x < W) ? img[((long long)c * H + y) * W + x] : 0.f;
   }
   __syncthreads();
-  const int nx = min(IM_XT, Wo - xo0), ny = min(IM_YT, Ho - yo0);
-  const int kreal = 49 * C;
-  const int per_row = nx * Kp;
-  for (int i = threadIdx.x; i < ny * per_row; i += 256) {
-    const int yl = i / per_row, rem = i - yl * per_row;
-    const int xl = rem / Kp, k = rem - xl * Kp;
-    float v = 0.f;
-    if (k < kreal) {
-      const int tap = k / C, c = k - tap * C;
-      const int ky = tap / 7, kx = tap - ky * 7;
-      v = patch[(c * PH + 2 * yl + ky) * PW + 2 * xl + kx];
+  const int nx = min(IM_XT, Wo - xo0);
+  const long long out_base = (((long long)b * Ho + yo) * Wo + xo0) * Kp;
+  const int kreal = 49 * C, K8 = Kp / 8;
+  for (int i = threadIdx.x; i < nx * K8; i += 256) {
+    const int xl = i / K8, k0 = (i - xl * K8) * 8;
+    float v[8], r[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + e;
+      float x = 0.f;
+      if (k < kreal) {
+        const int tap = k / C, c = k - tap * C;
+        const int ky = tap / 7, kx = tap - ky * 7;
+        x = patch[(c * 7 + ky) * PW + 2 * xl + kx];
+      }
+      v[e] = x;
+      r[e] = x - __half2float(__float2half_rn(x));
     }
-    const long long o = (((long long)b * Ho + yo0 + yl) * Wo + xo0) * Kp + rem;
-    const __half hv = __float2half_rn(v);
-    dst[o] = hv;
-    if (dst_lo) dst_lo[o] = __float2half_rn(v - __half2float(hv));
+    st8(dst + out_base + (long long)xl * Kp + k0, v, false);
+    if (dst_lo) st8(dst_lo + out_base + (long long)xl * Kp + k0, r, false);
   }
 }
 
 // ---------------------------------------------------------------- pooling / resampling (NHWC fp16, 8 channels per thread)
-__device__ __forceinline__ void ld8(const __half* p, float (&f)[8]) {
-  const uint4 v = *reinterpret_cast<const uint4*>(p);
-  const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) { const float2 t = __half22float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
-}
-__device__ __forceinline__ void st8(__half* p, const float (&f)[8], bool relu) {
-  uint4 v;
-  __half2* h = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-  for (int e = 0; e < 4; ++e)
-    h[e] = relu ? __floats2half2_rn(fmaxf(f[2 * e], 0.f), fmaxf(f[2 * e + 1], 0.f)) : __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-  *reinterpret_cast<uint4*>(p) = v;
-}
-
 // 3x3 stride-2 pad-1 max pool (resnet.py:123)
 __global__ void maxpool_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, __half* __restrict__ y,
                                __half* __restrict__ y_lo, int B, int H, int W, int C) {
@@ -466,8 +468,8 @@ int ew_nhwc_to_nchw(const __half* src, float* dst, int B, int C, int H, int W, c
 int ew_stem_im2col(const float* src, __half* dst, __half* dst_lo, int B, int C, int H, int W, int Kp, cudaStream_t s) {
   B200_REQUIRE(H % 2 == 0 && W % 2 == 0 && Kp % 64 == 0 && Kp >= 49 * C, "stem_im2col: bad shape");
   B200_REQUIRE(C >= 1 && C <= 8, "stem_im2col: at most 8 input planes");
-  const size_t smem = (size_t)C * (2 * ew::IM_YT + 5) * (2 * ew::IM_XT + 5) * sizeof(float);
-  ew::stem_im2col_kernel<<<dim3(ceil_div(W / 2, ew::IM_XT), B * ceil_div(H / 2, ew::IM_YT)), 256, smem, s>>>(src, dst, dst_lo, B, C, H, W, Kp);
+  const size_t smem = (size_t)C * 7 * (2 * ew::IM_XT + 5) * sizeof(float);
+  ew::stem_im2col_kernel<<<dim3(ceil_div(W / 2, ew::IM_XT), B * (H / 2)), 256, smem, s>>>(src, dst, dst_lo, B, C, H, W, Kp);
   B200_LAUNCH_CHECK();
   return 0;
 }
