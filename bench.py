@@ -263,6 +263,13 @@ def run_ours(args):
             'gpu_launches': int(launches), 'wall_ms_per_step': wall / args.steps, 'clocks': clocks,
             'cpu_baseline': cpu_baseline(wl, budget_s=25.0),
         }
+        if world == 1 and not args.no_torch_baseline:
+            del clip  # give the stock-PyTorch pass the whole device
+            torch.cuda.empty_cache()
+            try:
+                out['torch_gpu_baseline'] = torch_gpu_baseline(wl, device)
+            except Exception as exc:  # reported extra, never fatal for the bench line
+                out['torch_gpu_baseline'] = {'error': f'{type(exc).__name__}: {exc}'[:300]}
         print(json.dumps(out))
     if dist_on:
         dist.barrier()
@@ -270,62 +277,96 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------- CPU oracle
+def _oracle_stages(wl, budget_s, device, k_s):
+    """One frame of the reference algorithm (the oracle's fp32 PyTorch restatement) on ``device``, stage by stage.
+    Returns wall-clock seconds per stage; per-object stages run on ``k_s`` objects."""
+    from deva.model.param_spec import synthetic_state_dict
+    from oracle import memory_math as mm
+    from oracle import network as onet
+    from oracle.core import pad_to_multiple
+    cuda = torch.device(device).type == 'cuda'
+
+    def clock():
+        if cuda:
+            torch.cuda.synchronize()
+        return time.perf_counter()
+
+    sd = {name: v.to(device) for name, v in synthetic_state_dict(seed=0).items()}
+    t_all = time.perf_counter()
+    with torch.no_grad():
+        img, _ = pad_to_multiple(synth_frames(wl, 1, 7)[0], 16)
+        img = img.unsqueeze(0).to(device)
+        t0 = clock()
+        ms, feat = onet.encode_image(sd, img)
+        key, shr, sel = onet.transform_key(sd, feat)
+        t_shared = clock() - t0
+        h, w = key.shape[-2:]
+        n = wl['n']
+        g = torch.Generator().manual_seed(0)
+        mk, msh = torch.randn(CK, n, generator=g).to(device), (1 + torch.rand(n, generator=g)).to(device)
+        mv = torch.randn(k_s * CV, n, generator=g).to(device)
+        t0 = clock()
+        sim = mm.similarity(mk, msh, key[0].flatten(1), sel[0].flatten(1))
+        aff = mm.dense_affinity(sim, TOP_K)
+        t_aff = clock() - t0
+        t0 = clock()
+        ro = mm.readout(aff, mv)
+        t_ro = clock() - t0
+        del sim, aff
+        masks = synth_mask(wl)
+        masks = torch.stack([(masks == (i % wl['k']) + 1).float() for i in range(k_s)])
+        masks, _ = pad_to_multiple(masks, 16)
+        masks = masks.unsqueeze(0).to(device)
+        sens = torch.zeros(1, k_s, CV, h, w, device=device)
+        t0 = clock()
+        onet.segment(sd, ms, ro.view(1, k_s, CV, h, w), sens, masks)
+        t_seg = clock() - t0
+        t_enc = None
+        if time.perf_counter() - t_all < budget_s:
+            t0 = clock()
+            onet.encode_mask(sd, img, ms, sens, masks)
+            t_enc = clock() - t0
+    return {'encode': t_shared, 'affinity': t_aff, 'readout': t_ro, 'decode': t_seg, 'encode_mask': t_enc}
+
+
+def _blend(st, scale):
+    per_frame = st['encode'] + st['affinity'] + (st['readout'] + st['decode']) * scale
+    if st['encode_mask'] is not None:
+        per_frame += st['encode_mask'] * scale / 5.0
+    return per_frame
+
+
 def cpu_baseline(wl, budget_s):
     """Reference-algorithm frame rate on the host cores: the oracle's stages on a bounded sample.
 
     Object-independent stages run in full; per-object stages run on ``k_s`` of the K objects and are scaled by
     K/k_s (every per-object op is independent across objects)."""
-    from deva.model.param_spec import synthetic_state_dict
-    from oracle import memory_math as mm
-    from oracle import network as onet
-    from oracle.core import pad_to_multiple
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = synthetic_state_dict(seed=0)
-    t_all = time.perf_counter()
-    with torch.no_grad():
-        img, _ = pad_to_multiple(synth_frames(wl, 1, 7)[0], 16)
-        img = img.unsqueeze(0)
-        t0 = time.perf_counter()
-        ms, feat = onet.encode_image(sd, img)
-        key, shr, sel = onet.transform_key(sd, feat)
-        t_shared = time.perf_counter() - t0
-        h, w = key.shape[-2:]
-        q, n, k = h * w, wl['n'], wl['k']
-        k_s = 1
-        g = torch.Generator().manual_seed(0)
-        mk, msh = torch.randn(CK, n, generator=g), 1 + torch.rand(n, generator=g)
-        mv = torch.randn(k_s * CV, n, generator=g)
-        t0 = time.perf_counter()
-        sim = mm.similarity(mk, msh, key[0].flatten(1), sel[0].flatten(1))
-        aff = mm.dense_affinity(sim, TOP_K)
-        t_aff = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        ro = mm.readout(aff, mv)
-        t_ro = time.perf_counter() - t0
-        del sim, aff
-        masks = synth_mask(wl).unsqueeze(0)
-        masks, _ = pad_to_multiple((masks == 1).float(), 16)
-        masks = masks.unsqueeze(0)
-        sens = torch.zeros(1, k_s, CV, h, w)
-        t0 = time.perf_counter()
-        onet.segment(sd, ms, ro.view(1, k_s, CV, h, w), sens, masks)
-        t_seg = time.perf_counter() - t0
-        t_enc = None
-        if time.perf_counter() - t_all < budget_s:
-            t0 = time.perf_counter()
-            onet.encode_mask(sd, img, ms, sens, masks)
-            t_enc = time.perf_counter() - t0
+    k, k_s = wl['k'], 1
+    st = _oracle_stages(wl, budget_s, 'cpu', k_s)
     scale = k / k_s
-    per_frame = t_shared + t_aff + (t_ro + t_seg) * scale
-    if t_enc is not None:
-        per_frame += t_enc * scale / 5.0
-    return {'value': 1.0 / per_frame, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-            'sample': f'1 frame {wl["h"]}x{wl["w"]}, N={n}: encode_image+transform_key and similarity/top-k in full; '
-                      f'readout, decoder' + (', value encoder (1 frame in 5)' if t_enc is not None else '') +
+    return {'value': 1.0 / _blend(st, scale), 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+            'sample': f'1 frame {wl["h"]}x{wl["w"]}, N={wl["n"]}: encode_image+transform_key and similarity/top-k in '
+                      f'full; readout, decoder' + (', value encoder (1 frame in 5)' if st['encode_mask'] is not None else '') +
                       f' on {k_s} of {k} objects, scaled x{scale:g}; oracle = fp32 PyTorch-CPU port of the reference',
-            'stage_s': {'encode': t_shared, 'affinity': t_aff, 'readout_per_obj': t_ro, 'decode_per_obj': t_seg,
-                        'encode_mask_per_obj': t_enc}}
+            'stage_s': {'encode': st['encode'], 'affinity': st['affinity'], 'readout_per_obj': st['readout'],
+                        'decode_per_obj': st['decode'], 'encode_mask_per_obj': st['encode_mask']}}
+
+
+def torch_gpu_baseline(wl, device):
+    """SURVEY 8(d) "GPU-side comparison": the same reference algorithm as stock PyTorch ops (cuDNN / cuBLAS fp32,
+    PyTorch's default TF32 policy) on the same B200, all K objects in one batch.  Second of two passes (the first
+    pays cuDNN's algorithm selection).  A reported baseline only - none of it is on the product path."""
+    k = wl['k']
+    st = None
+    for _ in range(2):
+        st = _oracle_stages(wl, 1e9, device, k)
+        torch.cuda.empty_cache()
+    return {'value': 1.0 / _blend(st, 1.0), 'unit': 'frames/s', 'kind': 'oracle ops on cuda (stock PyTorch fp32)',
+            'tf32': {'cudnn': bool(torch.backends.cudnn.allow_tf32), 'matmul': bool(torch.backends.cuda.matmul.allow_tf32)},
+            'sample': f'1 frame {wl["h"]}x{wl["w"]}, N={wl["n"]}, all {k} objects; value encoder weighted 1 frame in 5',
+            'stage_s': st}
 
 
 def run_reference(args):
@@ -354,6 +395,7 @@ if __name__ == '__main__':
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c3', choices=list(WORKLOADS))
+    ap.add_argument('--no-torch-baseline', action='store_true', help='skip the stock-PyTorch-on-GPU comparison pass')
     a = ap.parse_args()
     if a.impl == 'reference':
         run_reference(a)

@@ -34,6 +34,13 @@ CASES = [
     (2, 16, 24, 256, 256, 3, 1),
     (1, 11, 19, 512, 129, 3, 1),   # key_proj-like ragged Cout (fp32 out)
     (2, 24, 40, 256, 1, 3, 1),     # pred-like single channel (fp32 out)
+    # enough tiles (>= 2 x 148) for the cluster launches: deep K -> tcgen05 CTA pairs (cta_group::2),
+    # shallow K -> weight multicast only; odd tile counts exercise the clamped "phantom" tile of a pair
+    (2, 136, 240, 128, 256, 3, 1),
+    (5, 67, 119, 192, 320, 3, 1),
+    (11, 100, 150, 128, 128, 3, 2),
+    (5, 72, 121, 1024, 256, 1, 1),
+    (3, 136, 241, 64, 256, 1, 1),
 ]
 
 

@@ -17,7 +17,7 @@
 //   + optional rank-1 term w1[cout] * x1[b, pixel] (the "+1" mask / logit input channel of
 //   sensory_compress and g4_conv), then writes any of: raw fp16, ReLU'd fp16, raw fp32.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..5 = epilogue.  Persistent CTAs, 4-stage
-//   smem ring, double-buffered accumulators.
+//   smem ring (6-stage in CTA-pair mode), double-buffered accumulators.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -34,9 +34,15 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES_MAX = 256 * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
+// CTA-pair mode (tcgen05 cta_group::2): each CTA stages its own 128 pixels and HALF of the weight tile, so a stage is
+// 32 KB instead of 48 KB and the same shared memory holds a 6-deep ring.
+constexpr int PAIR_STAGES = 6;
+constexpr int PAIR_STAGE_BYTES = A_BYTES + B_BYTES_MAX / 2;
+static_assert(PAIR_STAGES * PAIR_STAGE_BYTES == STAGES * STAGE_BYTES, "both modes share one shared-memory layout");
+constexpr int RING_BYTES = STAGES * STAGE_BYTES;
 constexpr int THREADS = 192;
 constexpr int HEAD_BYTES = kMaxHead * 256 * 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + HEAD_BYTES;
+constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256 + HEAD_BYTES;
 
 struct Params {
   int batch, ho, wo, cout;
@@ -75,6 +81,16 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
+      : "memory");
+}
+// CTA-pair variant: the data lands in THIS CTA's shared memory, the bytes are credited to the barrier of the pair's
+// leader (even) CTA -- its address is the local one with the peer bit (bit 24 of the shared-window address) cleared.
+__device__ __forceinline__ void tma_load_5d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, const int (&c)[5]) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]),
+      "r"(c[4])
       : "memory");
 }
 
@@ -117,21 +133,30 @@ __device__ __forceinline__ bool tile_decode(int u, int rank, const Params& p, in
   return real;
 }
 
+// PAIR = false: every CTA runs its own 128 x NT MMA (cta_group::1); clusters only share the weight tile by multicast.
+// PAIR = true : the two CTAs of a cluster form a tcgen05 CTA pair.  The leader (rank 0) issues ONE 256 x NT MMA
+//   (cta_group::2) per k-step: rows 0..127 are the leader's pixel tile and accumulate in the leader's TMEM, rows
+//   128..255 the peer's; each CTA holds half of the weight tile (NT/2 rows) and the tensor cores of both SMs read both
+//   halves.  Per SM the shared-memory operand traffic per MMA drops from 48 KB to 32 KB, which is what bounds the
+//   cta_group::1 kernel at ~80 % tensor-pipe utilisation.
+template <bool PAIR, bool HEAD>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p) {
+  constexpr int NST = PAIR ? PAIR_STAGES : STAGES;
+  constexpr int B_STRIDE = PAIR ? B_BYTES_MAX / 2 : B_BYTES_MAX;
   // 1024-byte alignment (128B swizzle atoms) comes from the declaration: deriving an aligned pointer through an
   // integer cast would make the compiler lose the shared address space (generic LD/ST instead of LDS/STS).
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* sB = smem + NST * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
   uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* acc_full = bars + 2 * STAGES;
+  uint64_t* empty = bars + NST;
+  uint64_t* acc_full = bars + 2 * NST;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_head = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [kMaxHead][256]
+  float* s_head = reinterpret_cast<float*>(smem + RING_BYTES + 256);  // [kMaxHead][256] fused-head weights
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,17 +166,23 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
   const int total_units = ((p.m_tiles + cs - 1) / cs) * p.n_tiles;
   const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
   const int k_iters = p.taps * p.cblocks;
-  const uint32_t stage_tx = A_BYTES + p.nt * BK * 2;
+  // PAIR: both CTAs' loads are credited to the leader's barrier -> it expects the bytes of both
+  const uint32_t stage_tx = PAIR ? 2 * (A_BYTES + (p.nt / 2) * BK * 2) : A_BYTES + p.nt * BK * 2;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 8; ++i) tma_prefetch_desc(&maps.act[i]);
     tma_prefetch_desc(&maps.wgt);
     tma_prefetch_desc(&maps.wgt_slice);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], cs); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    // empty[]: one tcgen05.commit arrive per MMA-issuing CTA that reads the stage (PAIR: the single pair MMA)
+    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], PAIR ? 1 : cs); }
+    // acc_empty[]: PAIR -> the leader's barrier collects the epilogue warps of both CTAs
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 8 : 4); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_2sm<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   if (cs > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
@@ -171,23 +202,31 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
           const CUtensorMap* am = &maps.act[p.tap_map[t]];
           for (int cb = 0; cb < p.cblocks; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], stage_tx);
             c[0] = cb * BK;
-            tma_load_5d(sA + stage * A_BYTES, am, &full[stage], c);
-            if (cs == 1) {
-              tma_load_2d(sB + stage * B_BYTES_MAX, &maps.wgt, &full[stage], (p.tap_w[t] * p.cblocks + cb) * BK, n0);
-            } else {  // this CTA fetches rows [rank*slice, +slice) of the weight tile for the whole cluster
-              tma_load_2d_mcast(sB + stage * B_BYTES_MAX + rank * slice_rows * 128, &maps.wgt_slice, &full[stage],
-                                (p.tap_w[t] * p.cblocks + cb) * BK, n0 + rank * slice_rows, cmask);
+            if constexpr (PAIR) {
+              // own pixels + own half of the weight rows, both at the same offsets in either CTA
+              if (rank == 0) mbar_expect_tx(&full[stage], stage_tx);
+              tma_load_5d_2sm(sA + stage * A_BYTES, am, &full[stage], c);
+              tma_load_2d_2sm(sB + stage * B_STRIDE, &maps.wgt_slice, &full[stage],
+                              (p.tap_w[t] * p.cblocks + cb) * BK, n0 + rank * slice_rows);
+            } else {
+              mbar_expect_tx(&full[stage], stage_tx);
+              tma_load_5d(sA + stage * A_BYTES, am, &full[stage], c);
+              if (cs == 1) {
+                tma_load_2d(sB + stage * B_STRIDE, &maps.wgt, &full[stage], (p.tap_w[t] * p.cblocks + cb) * BK, n0);
+              } else {  // this CTA fetches rows [rank*slice, +slice) of the weight tile for the whole cluster
+                tma_load_2d_mcast(sB + stage * B_STRIDE + rank * slice_rows * 128, &maps.wgt_slice, &full[stage],
+                                  (p.tap_w[t] * p.cblocks + cb) * BK, n0 + rank * slice_rows, cmask);
+              }
             }
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == NST) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(0, BM, p.nt);
+    if (lane == 0 && (!PAIR || rank == 0)) {
+      const uint32_t idesc = umma_idesc(0, PAIR ? 2 * BM : BM, p.nt);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -200,24 +239,31 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * B_BYTES_MAX);
+          const uint32_t b_addr = smem_u32(sB + stage * B_STRIDE);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                     (ki | k) != 0);
-          if (cs == 1) umma_commit(&empty[stage]);
+          for (int k = 0; k < BK / 16; ++k) {
+            if constexpr (PAIR)
+              umma_f16_2sm(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                           (ki | k) != 0);
+            else
+              umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                       (ki | k) != 0);
+          }
+          if constexpr (PAIR) umma_commit_2sm(&empty[stage], cmask);  // frees the stage in both CTAs
+          else if (cs == 1) umma_commit(&empty[stage]);
           else umma_commit_mcast(&empty[stage], cmask);  // the stage is free once EVERY CTA of the cluster has read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[acc]);
+        if constexpr (PAIR) umma_commit_2sm(&acc_full[acc], cmask);  // both CTAs' epilogues drain their half
+        else umma_commit(&acc_full[acc]);
       }
     }
   } else {
-    const int quad = warp & 3;
+    const int quad = warp & 3;         // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;  // pixel within the tile
     const int ty = row / p.tw, tx = row - ty * p.tw;
     const bool vec_ok = (p.cout % 8) == 0;
-    if (p.head_w) {  // stage the head weights once per CTA (epilogue warps only)
+    if constexpr (HEAD) {  // stage the head weights once per CTA (epilogue warps only), zero padded
       for (int i = threadIdx.x - 64; i < kMaxHead * 256; i += 128) {
         const int t = i / 256, ch = i - t * 256;
         s_head[i] = (t < p.head_n && ch < p.cout) ? p.head_w[t * p.cout + ch] : 0.f;
@@ -240,22 +286,22 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       float hacc[kMaxHead];
 #pragma unroll
       for (int t = 0; t < kMaxHead; ++t) hacc[t] = 0.f;
-      mbar_wait(&acc_full[acc], (it >> 1) & 1);
-      tc_fence_after();
       // Software pipeline over 32-channel chunks: the TMEM load and the residual loads of chunk c+1 are in flight
-      // while chunk c is finished (the residual comes from L2/HBM: ~1 us if waited for in place).
+      // while chunk c is finished (the residual comes from L2/HBM: ~1 us if waited for in place); the first chunk's
+      // residual is requested before the accumulator is even complete.
       const int n_chunks = p.nt / 32;
-      const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + acc * 256;
       const bool res_pf = res && live && vec_ok && (p.cout % 32 == 0);
       uint32_t r[32];
       uint4 res_cur[4], res_nxt[4];
-      tmem_ld_32x32(t_addr, r);
-      if (res_pf) {
+      if (res_pf && n0 + 32 <= p.cout) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) res_cur[j] = *reinterpret_cast<const uint4*>(res + j * 8);
       }
-#pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
+      mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + acc * 256;
+      tmem_ld_32x32(t_addr, r);
+      auto chunk = [&](const int c) {
         tmem_ld_wait();
         float v[32];
 #pragma unroll
@@ -311,7 +357,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
             }
             store_split(v, p.out_raw, p.out_raw_lo, off + c * 32, false);
             store_split(v, p.out_relu, p.out_relu_lo, off + c * 32, true);
-            if (p.head_w) {
+            if constexpr (HEAD) {  // logit head: 9 taps x 32 channels of this chunk, fp32, weights from shared memory
               float rv[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) rv[j] = fmaxf(v[j], 0.f);
@@ -362,11 +408,16 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) res_cur[j] = res_nxt[j];
-      }
+      };
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c) chunk(c);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (p.head_w && live) {
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster_relaxed(&acc_empty[acc], 0);  // tcgen05.ld are complete; no stores to publish
+        else mbar_arrive(&acc_empty[acc]);
+      }
+      if (HEAD && live) {
 #pragma unroll
         for (int t = 0; t < kMaxHead; ++t)
           if (t < p.head_n) p.head_out[pix * p.head_n + t] = hacc[t];
@@ -379,7 +430,8 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
   if (cs > 1) cluster_sync_all();  // nobody leaves while a peer may still multicast into this CTA
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_2sm<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -479,17 +531,27 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   }
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(conv_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(conv_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(conv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(conv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  // Cluster size: share the weight tile across 4 (or 2) CTAs when there is enough work to keep every SM busy.
+  // Clusters: with enough work to keep every SM busy, two CTAs either form a tcgen05 CTA pair (default) or only share
+  // the weight tile by TMA multicast (DEVA_B200_CONV_PAIR=0; DEVA_B200_CONV_CLUSTER=1/2/4 sets the multicast width).
   static const int max_cs = [] { const char* e = getenv("DEVA_B200_CONV_CLUSTER"); return e ? atoi(e) : 2; }();
+  static const bool want_pair = [] { const char* e = getenv("DEVA_B200_CONV_PAIR"); return e ? atoi(e) != 0 : true; }();
   int cs = 1;
   for (int c = max_cs; c >= 2; c >>= 1)
     if ((c == 2 || c == 4) && (d.nt / c) % 8 == 0 && (long long)p.m_tiles * p.n_tiles >= 2ll * sm_count() && sm_count() % c == 0) {
       cs = c;
       break;
     }
+  // the pair's cross-CTA handshakes only pay off with a deep K loop (short ones are latency/epilogue bound)
+  static const bool pair_head = [] { const char* e = getenv("DEVA_B200_CONV_PAIR_HEAD"); return e ? atoi(e) != 0 : true; }();
+  const bool pair = want_pair && cs >= 2 && (d.nt / 2) % 16 == 0 && p.taps * (d.cin_pad / 64) >= 16 &&
+                    (!d.head_w || pair_head);
+  if (pair) cs = 2;
   p.cs = cs;
   if (cs > 1 && make_tmap_2d(&maps.wgt_slice, TmapType::F16, d.w_packed, (uint64_t)w_groups * ktaps * d.cin_pad,
                              d.cout_pad, (uint64_t)w_groups * ktaps * d.cin_pad * 2, 64, d.nt / cs, &err)) {
@@ -510,14 +572,16 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
     a[0].val.clusterDim.x = cs; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
     q.attrs = a; q.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, conv_kernel, &q) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = sm_count() / cs; }
+    if (cudaOccupancyMaxActiveClusters(&n, conv_kernel<false, false>, &q) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = sm_count() / cs; }
     max_clusters[cs] = n;
   }
   long long clusters = cs > 1 ? max_clusters[cs] : sm_count();
   if (units < clusters) clusters = units;
   const int grid = (int)(clusters * cs);
+  const bool head = p.head_w != nullptr;
   if (cs == 1) {
-    conv_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(maps, p);
+    if (head) conv_kernel<false, true><<<grid, THREADS, SMEM_BYTES, stream>>>(maps, p);
+    else conv_kernel<false, false><<<grid, THREADS, SMEM_BYTES, stream>>>(maps, p);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -531,7 +595,10 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel, maps, p));
+    if (pair && head) B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<true, true>, maps, p));
+    else if (pair) B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<true, false>, maps, p));
+    else if (head) B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<false, true>, maps, p));
+    else B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<false, false>, maps, p));
   }
   B200_LAUNCH_CHECK();
   return 0;
