@@ -42,6 +42,21 @@ def bn(sd, name, x):
 net._conv = conv
 net._bn = bn
 
+# persistent state kept in fp16 by the native engine: the per-object sensory (hidden) state, the bank's values,
+# and the memory readout handed to the decoder
+STATE = dict(sensory=False, values=False, readout=False)
+orig_gru, orig_encode_mask, orig_readout = net._gru, net.encode_mask, mm.readout
+def gru(values, h, dim):
+    return rh(orig_gru(values, rh(h, STATE['sensory']), dim), STATE['sensory'])
+def encode_mask(*a, **k):
+    v, s = orig_encode_mask(*a, **k)
+    return rh(v, STATE['values']), s
+def readout(aff, mv):
+    return rh(orig_readout(rh(aff, STATE['readout']), rh(mv, STATE['values'])), STATE['readout'])
+net._gru = gru
+net.encode_mask = encode_mask
+mm.readout = readout
+
 def run(tag):
     g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(ROOT, 'tests/golden/vos_steps.npz')).items()}
     meta = json.load(open(os.path.join(ROOT, 'tests/golden/vos_steps.json')))
@@ -62,6 +77,19 @@ if __name__ == '__main__':
         for k in base: FLAGS[k] = False
         for n in names: FLAGS[n] = True
         FLAGS['weights'] = True
+    if len(sys.argv) > 1 and sys.argv[1] == 'state':
+        nat = ('maskenc', 'dec', 'up168', 'up84', 'gru')  # the native engine: key path + pred precise, rest fp16
+        only(*nat); run('native emulation, states fp32')
+        for combo in (('sensory',), ('values',), ('readout',), ('sensory', 'values', 'readout')):
+            for k in STATE: STATE[k] = k in combo
+            only(*nat); run('  + fp16 ' + '+'.join(combo))
+        for k in STATE: STATE[k] = False
+        only('maskenc', 'dec', 'up168', 'gru'); run('up_8_4 precise')
+        only('maskenc', 'dec', 'up84', 'gru'); run('up_16_8 precise')
+        only('maskenc', 'up168', 'up84', 'gru'); run('fuser/skip/compress precise')
+        only('dec', 'up168', 'up84', 'gru'); run('mask encoder precise')
+        only('maskenc', 'dec', 'up168', 'up84'); run('sensory update convs precise')
+        sys.exit(0)
     only('maskenc', 'dec', 'up168', 'up84', 'pred', 'gru'); run('key path (enc+key) precise, rest fp16')
     only('maskenc', 'dec', 'up168', 'up84', 'gru'); run('  + pred precise')
     only('maskenc', 'dec', 'up168', 'gru'); run('  + pred, up_8_4 precise')
