@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DEVA_B200_ABI_VERSION 6
+#define DEVA_B200_ABI_VERSION 7
 #define DEVA_B200_LIST_PITCH 32 /* row pitch of top-k outputs == max supported top_k */
 #define DEVA_B200_MAX_GROUPS 256 /* objects per deva_b200_readout call */
 
@@ -163,6 +163,12 @@ typedef struct deva_b200_conv_desc {
   const float* head_w;  /* optional fused 1x1 head on the ReLU'd fp32 result (needs cout_pad == nt): fp32 [head_n, cout] */
   float* head_out;      /* fp32 [batch*ho*wo, head_n]: head_out[p, t] = sum_c relu(out[p, c]) * head_w[t, c] */
   int32_t head_n;       /* <= 9.  Folds MaskDecoder.pred (big_modules.py:189-190) into the last decoder conv. */
+  /* optional fused gate epilogue (SensoryUpdater / SensoryDeepUpdater, modules.py:145-149,163-167): the conv output is
+   * never written; with C = cout/3 hidden channels the channel tile (nt must be 192) holds [forget | update | new] x 64
+   * for hidden channels 64*tile .. +63 (weight rows / bias packed in that order) and the epilogue writes
+   * gate_out = sigmoid(f) * gate_h * (1 - sigmoid(u)) + sigmoid(u) * tanh(n), evaluated on the fp32 accumulators. */
+  const void* gate_h;   /* fp16 NHWC [batch, ho, wo, cout/3] previous hidden state */
+  void* gate_out;       /* fp16 NHWC [batch, ho, wo, cout/3] new hidden state */
 } deva_b200_conv_desc;
 /* nn.Conv2d + folded BatchNorm (+ residual, + ReLU) as in deva/model/resnet.py:46-114, group_modules.py:41-67,
  * modules.py:22-39; `desc` is a HOST struct. */

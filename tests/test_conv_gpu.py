@@ -145,6 +145,28 @@ def test_conv_two_inputs():
     assert float((_nchw(out) - ref).abs().max()) < 2e-3
 
 
+@pytest.mark.parametrize('b,h,w', [(2, 9, 12), (16, 68, 60)])  # small: cta_group::1; large: CTA pairs
+def test_conv_gate_epilogue(b, h, w):
+    """Sensory update (modules.py:145-149): h' = f*h*(1-u) + u*tanh(n) from the fp32 accumulators of the 3x3 conv
+    over cat[g, h]; the 3C-channel conv output is never written."""
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(9)
+    c = 512
+    xg = torch.randn(b, c, h, w, device='cuda', generator=g)
+    xh = torch.randn(b, c, h, w, device='cuda', generator=g)
+    wgt = torch.randn(3 * c, 2 * c, 3, 3, device='cuda', generator=g) * (2.0 / (2 * c * 9))**0.5
+    bias = torch.randn(3 * c, device='cuda', generator=g)
+    pc = ops.PackedConv(wgt, bias, 1, two_inputs=True, gates=True)
+    gh, hh = _nhwc(xg), _nhwc(xh)
+    new_h = ops.conv_ex(gh, pc, x2=hh, gate_h=hh).hidden
+    xin = torch.cat([gh.float().permute(0, 3, 1, 2), hh.float().permute(0, 3, 1, 2)], 1)
+    v = F.conv2d(xin, wgt.half().float(), bias, padding=1)
+    f, u, n = torch.sigmoid(v[:, :c]), torch.sigmoid(v[:, c:2 * c]), torch.tanh(v[:, 2 * c:])
+    ref = f * hh.float().permute(0, 3, 1, 2) * (1 - u) + u * n
+    torch.cuda.synchronize()
+    assert float((_nchw(new_h) - ref).abs().max()) < 3e-3  # fp16 output rounding of |h'| <~ 4
+
+
 def test_conv_rank1_term():
     ops = _ops()
     g = torch.Generator(device='cuda').manual_seed(5)

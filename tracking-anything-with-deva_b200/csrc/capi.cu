@@ -109,6 +109,7 @@ DEVA_B200_API int deva_b200_conv2d(const deva_b200_conv_desc* c, deva_stream_t s
   d.out_raw = c->out_raw; d.out_relu = c->out_relu; d.out_f32 = c->out_f32;
   d.out_raw_lo = c->out_raw_lo; d.out_relu_lo = c->out_relu_lo;
   d.head_w = c->head_w; d.head_out = c->head_out; d.head_n = c->head_n;
+  d.gate_h = c->gate_h; d.gate_out = c->gate_out;
   return launch_conv(d, S(stream));
 }
 DEVA_B200_API int deva_b200_stem_im2col(const float* src, void* dst, void* dst_lo, int b, int c, int h, int w, int k_pad,

@@ -68,6 +68,9 @@ struct Params {
   const float* head_w;
   float* head_out;
   int head_n;
+  const __half* gate_h;  // EPI_GATES: previous hidden state [batch, ho, wo, gate_c]
+  __half* gate_out;
+  int gate_c;
 };
 
 struct Maps {
@@ -139,9 +142,16 @@ __device__ __forceinline__ bool tile_decode(int u, int rank, const Params& p, in
 //   128..255 the peer's; each CTA holds half of the weight tile (NT/2 rows) and the tensor cores of both SMs read both
 //   halves.  Per SM the shared-memory operand traffic per MMA drops from 48 KB to 32 KB, which is what bounds the
 //   cta_group::1 kernel at ~80 % tensor-pipe utilisation.
-template <bool PAIR, bool HEAD>
+// EPI selects the epilogue: plain (bias / residual / rank-1 / ReLU / outputs), plain + fused logit head, or the gated
+// hidden-state update of the sensory updaters.
+enum { EPI_PLAIN = 0, EPI_HEAD = 1, EPI_GATES = 2 };
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return 1.f / (1.f + __expf(-x)); }
+
+template <bool PAIR, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p) {
+  constexpr bool HEAD = EPI == EPI_HEAD;
   constexpr int NST = PAIR ? PAIR_STAGES : STAGES;
   constexpr int B_STRIDE = PAIR ? B_BYTES_MAX / 2 : B_BYTES_MAX;
   // 1024-byte alignment (128B swizzle atoms) comes from the declaration: deriving an aligned pointer through an
@@ -283,6 +293,57 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       const __half* res_lo = p.res_lo ? p.res_lo + (res - p.res) : nullptr;
       const float r1x = (p.rank1_x && live) ? p.rank1_x[pix] : 0.f;
       const int acc = it & 1;
+      if constexpr (EPI == EPI_GATES) {
+        // channel tile = [forget | update | new] x 64 for hidden channels hc0 .. hc0+63 (modules.py:145-149)
+        const int hc0 = (n0 / 192) * 64;
+        const long long hoff = pix * p.gate_c + hc0;
+        mbar_wait(&acc_full[acc], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + acc * 256;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t rf[32], ru[32], rn[32];
+          tmem_ld_32x32(t_addr + c * 32, rf);
+          tmem_ld_32x32(t_addr + 64 + c * 32, ru);
+          tmem_ld_32x32(t_addr + 128 + c * 32, rn);
+          uint4 hv[4];
+          if (live) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hv[j] = *reinterpret_cast<const uint4*>(p.gate_h + hoff + c * 32 + j * 8);
+          }
+          tmem_ld_wait();
+          if (live) {
+            const float* bf = p.bias + n0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 ov;
+              __half2* o2 = reinterpret_cast<__half2*>(&ov);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&hv[j]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int ch = j * 8 + 2 * e;
+                const float2 hp = __half22float2(h2[e]);
+                float o[2];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                  const float f = sigmoid_fast(__uint_as_float(rf[ch + s]) + bf[ch + s]);
+                  const float u = sigmoid_fast(__uint_as_float(ru[ch + s]) + bf[64 + ch + s]);
+                  const float n = tanhf(__uint_as_float(rn[ch + s]) + bf[128 + ch + s]);
+                  o[s] = f * (s ? hp.y : hp.x) * (1.f - u) + u * n;
+                }
+                o2[e] = __floats2half2_rn(o[0], o[1]);
+              }
+              *reinterpret_cast<uint4*>(p.gate_out + hoff + c * 32 + j * 8) = ov;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster_relaxed(&acc_empty[acc], 0);
+          else mbar_arrive(&acc_empty[acc]);
+        }
+      } else {
       float hacc[kMaxHead];
 #pragma unroll
       for (int t = 0; t < kMaxHead; ++t) hacc[t] = 0.f;
@@ -422,6 +483,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
         for (int t = 0; t < kMaxHead; ++t)
           if (t < p.head_n) p.head_out[pix * p.head_n + t] = hacc[t];
       }
+      }  // plain / head epilogue
     }
   }
 
@@ -524,6 +586,14 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   p.out_f32 = d.out_f32;
   p.out_raw_lo = reinterpret_cast<__half*>(d.out_raw_lo);
   p.out_relu_lo = reinterpret_cast<__half*>(d.out_relu_lo);
+  if (d.gate_out) {
+    B200_REQUIRE(d.gate_h && d.nt == 192 && d.cout == d.cout_pad && d.cout % 192 == 0 && !d.head_w && !d.res && !d.rank1_w &&
+                     !d.out_raw && !d.out_relu && !d.out_f32,
+                 "conv: the gate epilogue needs nt == 192, cout = 3 * C with C %% 64 == 0 (got %d) and no other outputs", d.cout);
+    p.gate_h = reinterpret_cast<const __half*>(d.gate_h);
+    p.gate_out = reinterpret_cast<__half*>(d.gate_out);
+    p.gate_c = d.cout / 3;
+  }
   if (d.head_w) {
     B200_REQUIRE(d.cout_pad == d.nt && d.cout % 32 == 0 && d.cout <= 256 && d.head_n >= 1 && d.head_n <= kMaxHead && d.head_out,
                  "conv: fused head needs the whole Cout (%d) in one channel tile and head_n <= %d", d.cout, kMaxHead);
@@ -531,10 +601,12 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   }
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(conv_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    B200_CUDA(cudaFuncSetAttribute(conv_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    B200_CUDA(cudaFuncSetAttribute(conv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    B200_CUDA(cudaFuncSetAttribute(conv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(conv_kernel<false, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(conv_kernel<true, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(conv_kernel<false, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(conv_kernel<true, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(conv_kernel<false, EPI_GATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(conv_kernel<true, EPI_GATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   // Clusters: with enough work to keep every SM busy, two CTAs either form a tcgen05 CTA pair (default) or only share
@@ -572,16 +644,17 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
     a[0].val.clusterDim.x = cs; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
     q.attrs = a; q.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, conv_kernel<false, false>, &q) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = sm_count() / cs; }
+    if (cudaOccupancyMaxActiveClusters(&n, conv_kernel<false, EPI_PLAIN>, &q) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = sm_count() / cs; }
     max_clusters[cs] = n;
   }
   long long clusters = cs > 1 ? max_clusters[cs] : sm_count();
   if (units < clusters) clusters = units;
   const int grid = (int)(clusters * cs);
-  const bool head = p.head_w != nullptr;
+  const int epi = p.gate_out ? EPI_GATES : (p.head_w ? EPI_HEAD : EPI_PLAIN);
   if (cs == 1) {
-    if (head) conv_kernel<false, true><<<grid, THREADS, SMEM_BYTES, stream>>>(maps, p);
-    else conv_kernel<false, false><<<grid, THREADS, SMEM_BYTES, stream>>>(maps, p);
+    if (epi == EPI_GATES) conv_kernel<false, EPI_GATES><<<grid, THREADS, SMEM_BYTES, stream>>>(maps, p);
+    else if (epi == EPI_HEAD) conv_kernel<false, EPI_HEAD><<<grid, THREADS, SMEM_BYTES, stream>>>(maps, p);
+    else conv_kernel<false, EPI_PLAIN><<<grid, THREADS, SMEM_BYTES, stream>>>(maps, p);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -595,10 +668,15 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (pair && head) B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<true, true>, maps, p));
-    else if (pair) B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<true, false>, maps, p));
-    else if (head) B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<false, true>, maps, p));
-    else B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<false, false>, maps, p));
+    if (pair) {
+      if (epi == EPI_GATES) B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<true, EPI_GATES>, maps, p));
+      else if (epi == EPI_HEAD) B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<true, EPI_HEAD>, maps, p));
+      else B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<true, EPI_PLAIN>, maps, p));
+    } else {
+      if (epi == EPI_GATES) B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<false, EPI_GATES>, maps, p));
+      else if (epi == EPI_HEAD) B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<false, EPI_HEAD>, maps, p));
+      else B200_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<false, EPI_PLAIN>, maps, p));
+    }
   }
   B200_LAUNCH_CHECK();
   return 0;

@@ -33,6 +33,9 @@ struct ConvDesc {
   const float* head_w;   // [head_n, cout] fp32
   float* head_out;       // [batch*ho*wo, head_n] fp32
   int head_n;
+  // optional fused gate epilogue (see include/deva_b200.h): h' = f*h*(1-u) + u*tanh(n) on the fp32 accumulators
+  const void* gate_h;
+  void* gate_out;
 };
 
 int launch_conv(const ConvDesc& d, cudaStream_t stream);

@@ -61,7 +61,7 @@ class NativeEngine:
             elif precise:
                 P[name] = ops.PackedConv(spec.weight, spec.bias, spec.stride, precise=True)
             elif name.endswith('.gru'):
-                P[name] = ops.PackedConv(spec.weight, spec.bias, 1, two_inputs=True)
+                P[name] = ops.PackedConv(spec.weight, spec.bias, 1, two_inputs=True, gates=True)
             elif name.endswith('.sensory_compress'):
                 P[name] = ops.PackedConv(spec.weight, spec.bias, 1, rank1_in=spec.weight.shape[1] - 1)
             elif name.endswith('.su.g4_conv'):
@@ -146,8 +146,9 @@ class NativeEngine:
         return ops.conv(y, P[p + '.b2.c2'], res=gr_raw, want_raw=True)
 
     def _gru(self, key, g, h):
-        values = ops.conv(g, self.P[key], x2=h, want_raw=True)
-        return ops.gru(values, h)
+        # 3x3 conv over cat[g, h] -> (forget, update, new) gates -> h' (modules.py:145-149,163-167), one kernel:
+        # the gates are evaluated on the fp32 accumulators in the conv epilogue, the 3C-channel tensor is never stored
+        return ops.conv_ex(g, self.P[key], x2=h, gate_h=h).hidden
 
     # ------------------------------------------------------------------ value encoder (a13)
     def _basic(self, x, q):

@@ -29,10 +29,20 @@ def _round_up(x, m):
 class PackedConv:
     """One convolution ready for ``deva_b200_conv2d``."""
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int,
-                 rank1_in: Optional[int] = None, two_inputs: bool = False, precise: bool = False):
+                 rank1_in: Optional[int] = None, two_inputs: bool = False, precise: bool = False,
+                 gates: bool = False):
         """weight [Cout, Cin, k, k] fp32 (BN folded); if ``rank1_in`` is given, that input channel is split
-        off as a rank-1 term (out += w[:, rank1_in] * x1) - used for the '+1' mask / logit channels."""
+        off as a rank-1 term (out += w[:, rank1_in] * x1) - used for the '+1' mask / logit channels.
+        ``gates``: Cout = [forget | update | new] x C of a sensory updater; rows are regrouped so that every
+        192-channel tile holds the three gates of 64 hidden channels and the conv epilogue applies the update."""
         cout, cin, kh, kw = weight.shape
+        self.gates = gates
+        if gates:
+            c_hidden = cout // 3
+            assert cout == 3 * c_hidden and c_hidden % 64 == 0
+            order = torch.arange(cout, device=weight.device).view(3, c_hidden // 64, 64).permute(1, 0, 2).reshape(-1)
+            weight = weight[order]
+            bias = bias[order] if bias is not None else None
         assert kh == kw and kh in (1, 3)
         dev = weight.device
         self.rank1_w = None
@@ -50,7 +60,9 @@ class PackedConv:
             cin //= 2
         self.cout, self.cin, self.k, self.stride = cout, cin, kh, stride
         self.cin_pad = _round_up(cin, 64)
-        if cout >= 256:
+        if gates:
+            self.nt = 192
+        elif cout >= 256:
             self.nt = 256 if cout % 256 == 0 else (128 if cout % 128 == 0 else 0)
         else:
             self.nt = _round_up(cout, 32)
@@ -81,16 +93,17 @@ class PackedConv:
 
 
 class ConvOut:
-    __slots__ = ('raw', 'raw_lo', 'relu', 'relu_lo', 'f32', 'head')
+    __slots__ = ('raw', 'raw_lo', 'relu', 'relu_lo', 'f32', 'head', 'hidden')
 
     def __init__(self):
-        self.raw = self.raw_lo = self.relu = self.relu_lo = self.f32 = self.head = None
+        self.raw = self.raw_lo = self.relu = self.relu_lo = self.f32 = self.head = self.hidden = None
 
 
 def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = None, x_lo: Optional[torch.Tensor] = None,
             res: Optional[torch.Tensor] = None, res_lo: Optional[torch.Tensor] = None,
             rank1_x: Optional[torch.Tensor] = None, want_raw: bool = False, want_relu: bool = False,
-            want_f32: bool = False, want_lo: bool = False, head_w: Optional[torch.Tensor] = None) -> ConvOut:
+            want_f32: bool = False, want_lo: bool = False, head_w: Optional[torch.Tensor] = None,
+            gate_h: Optional[torch.Tensor] = None) -> ConvOut:
     """x fp16 NHWC [B,H,W,cin_pad] (+ x2: implicit channel concat, or + x_lo: split precision) -> ConvOut."""
     assert x.dtype == torch.float16 and x.is_contiguous() and x.shape[-1] == pc.cin_pad, (x.shape, pc.cin_pad)
     assert (x2 is not None) == pc.two_inputs and (x_lo is not None) == pc.precise
@@ -127,10 +140,16 @@ def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = Non
         head_n = head_w.shape[0]
         assert head_w.dtype == torch.float32 and head_w.is_contiguous() and head_w.shape[1] == pc.cout
         o.head = torch.empty(b, ho, wo, head_n, dtype=torch.float32, device=dev)
+    assert (gate_h is not None) == pc.gates
+    if gate_h is not None:  # fused hidden-state update: the conv output itself is never written
+        assert gate_h.dtype == torch.float16 and gate_h.is_contiguous() and gate_h.shape == (b, ho, wo, pc.cout // 3)
+        assert not (want_raw or want_relu or want_f32 or res is not None or head_w is not None)
+        o.hidden = torch.empty_like(gate_h)
     nat.conv2d(x, b, h, w, pc.cin_pad, pc.w_packed, pc.k, pc.stride, pc.cout, pc.cout_pad, pc.nt, th, tw, pc.bias,
                x2=x2, x_lo=x_lo, res=res, res_lo=res_lo, res_broadcast=res_b, rank1_w=pc.rank1_w,
                rank1_x=rank1_x if pc.rank1_w is not None else None, out_raw=o.raw, out_relu=o.relu, out_f32=o.f32,
-               out_raw_lo=o.raw_lo, out_relu_lo=o.relu_lo, head_w=head_w, head_out=o.head, head_n=head_n)
+               out_raw_lo=o.raw_lo, out_relu_lo=o.relu_lo, head_w=head_w, head_out=o.head, head_n=head_n,
+               gate_h=gate_h, gate_out=o.hidden)
     return o
 
 
