@@ -160,9 +160,92 @@ def golden_vos():
     print('  sizes', sizes[-1], 'prob range', float(probs[-1].min()), float(probs[-1].max()))
 
 
+def golden_consensus():
+    """In-clip consensus (consensus_associated.py / consensus_automatic.py) on the seeded scenario of
+    consensus_scenario.py.  `pulp` is absent: the reference's fallback-solver hook `solve_with_pulp` gets an exact
+    enumeration of its own integer program (ascending bitmask order, first strictly better selection wins)."""
+    sys.path.insert(0, HERE)
+    import consensus_scenario as sc
+    import deva.inference.consensus_automatic as CA
+    from deva.inference.consensus_associated import find_consensus_with_established_association, spatial_alignment
+    from deva.inference.frame_utils import FrameInfo
+    from deva.inference.image_feature_store import ImageFeatureStore
+    from deva.inference.object_info import ObjectInfo
+    from deva.utils.tensor_utils import pad_divide_by
+
+    def brute(pairwise_iou, indicator, total):
+        w = [float(pairwise_iou[:, i].sum() * 2) - 1.0 for i in range(total)]
+        conflicts = [(i, j) for i in range(total) for j in range(i + 1, total) if indicator[i, j]]
+        best_v, best_x = 0.0, 0
+        for x in range(1, 1 << total):
+            if any((x >> i) & 1 and (x >> j) & 1 for i, j in conflicts):
+                continue
+            v = sum(w[i] for i in range(total) if (x >> i) & 1)
+            if v > best_v + 1e-9:
+                best_v, best_x = v, x
+        return [bool((best_x >> i) & 1) for i in range(total)]
+
+    CA.use_gurobi = False
+    CA.solve_with_pulp = brute
+    sd = param_spec.synthetic_state_dict(seed=1)
+    net = DEVA(CFG).eval()
+    net.load_weights(sd)
+    data = sc.frames()
+
+    def frame_infos():
+        out = []
+        for ti, (image, ids), dets in zip(sc.TIMES, data, sc.DETECTIONS):
+            infos = [ObjectInfo(sid, category_id=cat, isthing=thing, score=score) for sid, _, cat, thing, score in dets]
+            out.append(FrameInfo(image, ids, infos, ti, {}))
+        return out
+
+    arrays, meta = {}, {'config': CFG, 'auto': {}}
+    # (1) spatial_alignment frame 0 -> frame 1, two objects
+    store = ImageFeatureStore(net, no_warning=True)
+    img0, pads = pad_divide_by(data[0][0], 16)
+    img1, _ = pad_divide_by(data[1][0], 16)
+    m0, _ = pad_divide_by(torch.stack([data[0][1] == 3, data[0][1] == 5]).float(), 16)
+    arrays['align_prob'] = spatial_alignment(10, img0, m0, 11, img1, net, store, CFG)[0]
+    # (2) established association over frames 0, 1, 3 (channels: object A, object B)
+    store = ImageFeatureStore(net, no_warning=True)
+    pick = [(0, (3, 5)), (1, (1, 4)), (3, (7, 8))]
+    images = [data[i][0].clone() for i, _ in pick]
+    masks = [torch.stack([data[i][1] == a, data[i][1] == b]).float() for i, (a, b) in pick]
+    kti, total = find_consensus_with_established_association([sc.TIMES[i] for i, _ in pick], images, masks, net, store, CFG)
+    arrays['established_mask'] = total
+    meta['established_keyframe'] = kti
+    kti, total = find_consensus_with_established_association([sc.TIMES[i] for i, _ in pick],
+                                                            [data[i][0].clone() for i, _ in pick],
+                                                            [torch.stack([data[i][1] == a, data[i][1] == b]).float()
+                                                             for i, (a, b) in pick], net,
+                                                            ImageFeatureStore(net, no_warning=True), CFG,
+                                                            scores=[0.2, 0.9, 0.5])
+    arrays['established_mask_scored'] = total
+    meta['established_keyframe_scored'] = kti
+
+    # (3) automatic association, the real projection
+    def run(tag, keyframe):
+        kti, mask, infos = CA.find_consensus_auto_association(frame_infos(), keyframe, network=net,
+                                                              store=ImageFeatureStore(net, no_warning=True), config=CFG)
+        arrays[f'auto_{tag}_mask'] = mask
+        meta['auto'][tag] = {'keyframe': kti, 'segments': [[o.id, o.category_ids, o.scores] for o in infos]}
+        print('  consensus', tag, kti, [o.id for o in infos], 'ids in mask', mask.unique().tolist())
+
+    run('real_first', 'first')
+    # (4) automatic association on prescribed projections: pins matching / selection / merging / painting
+    real = CA.spatial_alignment
+    CA.spatial_alignment = lambda *a: sc.shifted_alignment(*a[:5])
+    for keyframe in ('first', 'last', 'middle'):
+        run('shifted_' + keyframe, keyframe)
+    CA.spatial_alignment = real
+    save('consensus.npz', **arrays)
+    json.dump(meta, open(os.path.join(HERE, 'consensus.json'), 'w'))
+
+
 if __name__ == '__main__':
     golden_spec()
     golden_memory_read()
     golden_bank_trace()
     golden_network()
     golden_vos()
+    golden_consensus()

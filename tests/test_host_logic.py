@@ -128,6 +128,24 @@ def test_match_and_merge_matches_reference_logic():
         assert om.find_object_by_id(11).poke_count == 1
 
 
+def test_consensus_selection_is_optimal():
+    """solve_exact (no ILP solver needed) == exhaustive enumeration of the reference's integer program
+    (consensus_automatic.py:28-79) on random conflict graphs, including the tie-breaking rule."""
+    import numpy as np
+    from deva.inference.consensus_automatic import solve_exact
+    from oracle.consensus import solve_brute_force
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        n = int(rng.integers(1, 12))
+        iou = np.zeros((n, n), dtype=np.float32)
+        for i in range(n):
+            for j in range(i + 1, n):
+                if rng.random() < 0.25:
+                    iou[i, j] = iou[j, i] = np.float32(rng.choice([0.55, 0.6, 0.75, 0.9]) if trial % 2 else rng.uniform(0.5, 1))
+        ind = iou > 0.49
+        assert solve_exact(iou * ind, ind, n) == solve_brute_force(iou * ind, ind, n), (trial, iou)
+
+
 def test_c_abi_exports_every_declared_symbol():
     lib_path = os.path.join(ROOT, 'tracking-anything-with-deva_b200', 'csrc', 'libdeva_b200.so')
     if not os.path.exists(lib_path):

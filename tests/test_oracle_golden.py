@@ -100,3 +100,58 @@ def test_bank_trace_matches_reference(golden_dir):
             mem.read(key, sel)
         mem.add(key, shr, torch.randn(1, len(objs), 8, h, w), list(objs), selection=sel)
         assert {str(b): list(s) for b, s in mem.sizes().items()} == want, t
+
+
+# ---------------------------------------------------------------------------- in-clip consensus
+def _scenario(golden_dir):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('consensus_scenario', os.path.join(golden_dir, 'consensus_scenario.py'))
+    sc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sc)
+    return sc
+
+
+def test_consensus_alignment_matches_reference(golden_dir, synthetic_sd):
+    from oracle import consensus as oc
+    from oracle.core import pad_to_multiple
+    sc = _scenario(golden_dir)
+    g = _load(golden_dir, 'consensus.npz')
+    meta = json.load(open(os.path.join(golden_dir, 'consensus.json')))
+    cfg, data = meta['config'], sc.frames()
+    img0, _ = pad_to_multiple(data[0][0], 16)
+    img1, _ = pad_to_multiple(data[1][0], 16)
+    m0, _ = pad_to_multiple(torch.stack([data[0][1] == 3, data[0][1] == 5]).float(), 16)
+    prob = oc.spatial_alignment(synthetic_sd, img0, m0, img1, cfg)[0]
+    torch.testing.assert_close(prob, g['align_prob'], rtol=1e-4, atol=2e-5)
+    pick = [(0, (3, 5)), (1, (1, 4)), (3, (7, 8))]
+    for key, scores in (('established_mask', None), ('established_mask_scored', [0.2, 0.9, 0.5])):
+        kti, total = oc.established_association(
+            synthetic_sd, [sc.TIMES[i] for i, _ in pick], [data[i][0] for i, _ in pick],
+            [torch.stack([data[i][1] == a, data[i][1] == b]).float() for i, (a, b) in pick], cfg, scores=scores)
+        assert kti == meta['established_keyframe' + ('_scored' if scores else '')]
+        torch.testing.assert_close(total, g[key], rtol=1e-4, atol=2e-5)
+
+
+def test_consensus_voting_matches_reference(golden_dir, synthetic_sd):
+    """Matching (IoU > 0.5, same isthing), exact selection, meta merging and painting order: bit-exact ids."""
+    from oracle import consensus as oc
+    sc = _scenario(golden_dir)
+    g = _load(golden_dir, 'consensus.npz')
+    meta = json.load(open(os.path.join(golden_dir, 'consensus.json')))
+    data = sc.frames()
+
+    def frames():
+        return [(ti, image, ids, [oc.Segment(sid, cat, thing, score) for sid, _, cat, thing, score in dets])
+                for ti, (image, ids), dets in zip(sc.TIMES, data, sc.DETECTIONS)]
+
+    for keyframe in ('first', 'last', 'middle'):
+        kti, mask, infos = oc.auto_association(frames(), keyframe, sc.shifted_alignment)
+        want = meta['auto']['shifted_' + keyframe]
+        assert kti == want['keyframe']
+        assert [list(i) for i in infos] == want['segments']
+        assert torch.equal(mask, g[f'auto_shifted_{keyframe}_mask'])
+    kti, mask, infos = oc.auto_association(
+        frames(), 'first', lambda sti, si, sm, tti, tim: oc.spatial_alignment(synthetic_sd, si, sm, tim, meta['config']))
+    want = meta['auto']['real_first']
+    assert kti == want['keyframe'] and [list(i) for i in infos] == want['segments']
+    assert torch.equal(mask, g['auto_real_first_mask'])

@@ -9,6 +9,7 @@ from typing import Dict, Iterable, List, Literal, Optional
 
 import torch
 
+from deva.inference.consensus_automatic import find_consensus_auto_association
 from deva.inference.frame_utils import FrameInfo
 from deva.inference.image_feature_store import ImageFeatureStore
 from deva.inference.memory_manager import MemoryManager
@@ -86,11 +87,12 @@ class DEVAInferenceCore:
     def add_to_temporary_buffer(self, frame_info: FrameInfo) -> None:
         self.frame_buffer.append(frame_info)
 
-    def vote_in_temporary_buffer(self, keyframe_selection: Literal['last', 'middle', 'score', 'first'] = 'first'):
-        # In-clip consensus (deva/inference/consensus_automatic.py) is the first "next" row of the
-        # scope table; it needs an ILP solver that is not part of the hot path.
-        raise NotImplementedError('in-clip consensus (find_consensus_auto_association) is not part of the '
-                                  'propagation hot path built here')
+    def vote_in_temporary_buffer(self, keyframe_selection: Literal['last', 'middle', 'score', 'first'] = 'first'
+                                 ) -> (int, torch.Tensor, List[ObjectInfo]):
+        """In-clip consensus over the buffered detections (inference_core.py:118-130)."""
+        return find_consensus_auto_association(self.frame_buffer, network=self.network,
+                                               store=self.image_feature_store, config=self.config,
+                                               keyframe_selection=keyframe_selection)
 
     def clear_buffer(self) -> None:
         for f in self.frame_buffer:

@@ -53,6 +53,7 @@ class MemoryManager:
         # 'nhwc': match_memory returns fp16 token-major-backed views (what the native NHWC decoder consumes)
         self.readout_layout = 'nchw'
         self.fused_min_work = 16_000_000  # n_window * q above which the fused sparse-affinity readout is used
+        self.work_frames_without_long_term = 16  # bank capacity (frames) when long-term memory is disabled
 
     def _read_long_term_config(self, config: Dict) -> None:
         self.max_mem_frames = config['max_mid_term_frames']
@@ -221,7 +222,7 @@ class MemoryManager:
             if self.use_long_term:
                 long_cap, work_cap = self.max_long_tokens, self.max_work_tokens + n
             else:
-                long_cap, work_cap = 0, 16 * n
+                long_cap, work_cap = 0, self.work_frames_without_long_term * n
             self._banks[b] = BucketBank(ids, self.CK, self.CV, long_cap, work_cap, key.device)
             per_bank[b] = {objects[i]: value[i] for i in fresh}
         for b, vals in per_bank.items():
