@@ -212,6 +212,19 @@ DEVA_B200_API int deva_b200_head_gather3x3(const float* z, float* out, float bia
 DEVA_B200_API int deva_b200_transpose_append(const void* src, void* dst, int64_t ld_dst, int n, int c,
                                              deva_stream_t stream);
 
+/* ---- frame ingest / egress ------------------------------------------------------------------------ */
+/* Decoded frame u8 [h, w, 3] (RGB interleaved) -> fp32 [3, h, w], (x / 255 - mean[c]) / std[c]: torchvision's
+ * ToTensor + Normalize (deva/inference/data/video_reader.py:146-150) after the upload instead of before it (4x fewer
+ * PCIe bytes).  Bit-exact with the torch ops (IEEE divisions in the same order). */
+DEVA_B200_API int deva_b200_ingest_rgb8(const uint8_t* src, float* dst, int h, int w, const float mean[3],
+                                        const float std[3], deva_stream_t stream);
+/* Driver post-step (evaluation/eval_vos.py:169-181) in one pass: optional bilinear resize (align_corners=False) of
+ * prob fp32 [c, h, w] to [out_h, out_w], optional horizontal flip, argmax over channels (first maximum wins),
+ * temporary-id -> object-id remap through lut int32 [c] (lut[0] = 0).  Writes out_u8 [out_h, out_w] and/or
+ * out_i64 [out_h, out_w] (either may be NULL). */
+DEVA_B200_API int deva_b200_prob_to_ids(const float* prob, int c, int h, int w, int out_h, int out_w, int flip,
+                                        const int32_t* lut, uint8_t* out_u8, int64_t* out_i64, deva_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

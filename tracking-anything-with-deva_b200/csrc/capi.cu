@@ -162,5 +162,13 @@ DEVA_B200_API int deva_b200_transpose_append(const void* src, void* dst, int64_t
                                              deva_stream_t stream) {
   return ew_transpose_append(H(src), H(dst), ld_dst, n, c, S(stream));
 }
+DEVA_B200_API int deva_b200_ingest_rgb8(const uint8_t* src, float* dst, int h, int w, const float mean[3],
+                                        const float std[3], deva_stream_t stream) {
+  return ew_ingest_rgb8(src, dst, h, w, mean, std, S(stream));
+}
+DEVA_B200_API int deva_b200_prob_to_ids(const float* prob, int c, int h, int w, int out_h, int out_w, int flip,
+                                        const int32_t* lut, uint8_t* out_u8, int64_t* out_i64, deva_stream_t stream) {
+  return ew_prob_to_ids(prob, c, h, w, out_h, out_w, flip, lut, out_u8, reinterpret_cast<long long*>(out_i64), S(stream));
+}
 
 }  // extern "C"

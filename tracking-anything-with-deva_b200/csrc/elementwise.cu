@@ -540,6 +540,76 @@ int ew_head_gather3x3(const float* z, float* out, float bias, int B, int H, int 
   B200_LAUNCH_CHECK();
   return 0;
 }
+// ---------------------------------------------------------------- frame ingest / egress
+namespace ew {
+// u8 [h, w, 3] -> fp32 [3, h, w]: ToTensor (x / 255) then Normalize ((x - mean) / std), IEEE divisions like torch
+__global__ void __launch_bounds__(256)
+ingest_rgb8_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, long long hw, float m0, float m1,
+                   float m2, float s0, float s1, float s2) {
+  const long long i = blockIdx.x * 256ll + threadIdx.x;
+  if (i >= hw) return;
+  const unsigned char* p = src + 3 * i;
+  dst[i] = __fdiv_rn(__fdiv_rn((float)p[0], 255.f) - m0, s0);
+  dst[hw + i] = __fdiv_rn(__fdiv_rn((float)p[1], 255.f) - m1, s1);
+  dst[2 * hw + i] = __fdiv_rn(__fdiv_rn((float)p[2], 255.f) - m2, s2);
+}
+
+// prob [c, h, w] -> ids [out_h, out_w]: bilinear (align_corners = False, PyTorch's upsample_bilinear2d arithmetic),
+// flip, argmax (first maximum), id remap.  One thread per output pixel, channels streamed.
+__global__ void __launch_bounds__(256)
+prob_to_ids_kernel(const float* __restrict__ prob, int c, int h, int w, int out_h, int out_w, int flip, float rh,
+                   float rw, const int* __restrict__ lut, unsigned char* __restrict__ out_u8,
+                   long long* __restrict__ out_i64) {
+  const long long i = blockIdx.x * 256ll + threadIdx.x;
+  if (i >= (long long)out_h * out_w) return;
+  const int oy = (int)(i / out_w), ox_out = (int)(i - (long long)oy * out_w);
+  const int ox = flip ? out_w - 1 - ox_out : ox_out;  // flip acts on the resized map
+  int best = 0;
+  float best_v;
+  const long long plane = (long long)h * w;
+  if (out_h == h && out_w == w) {
+    const float* p = prob + (long long)oy * w + ox;
+    best_v = p[0];
+    for (int k = 1; k < c; ++k) {
+      const float v = p[k * plane];
+      if (v > best_v) { best_v = v; best = k; }
+    }
+  } else {
+    const float sy = fmaxf(rh * (oy + 0.5f) - 0.5f, 0.f), sx = fmaxf(rw * (ox + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int yp = y0 < h - 1 ? 1 : 0, xp = x0 < w - 1 ? 1 : 0;
+    const float ly1 = sy - y0, ly0 = 1.f - ly1, lx1 = sx - x0, lx0 = 1.f - lx1;
+    const float* p = prob + (long long)y0 * w + x0;
+    best_v = -INFINITY;
+    for (int k = 0; k < c; ++k) {
+      const float* q = p + k * plane;
+      const float v = ly0 * (lx0 * q[0] + lx1 * q[xp]) + ly1 * (lx0 * q[yp * w] + lx1 * q[yp * w + xp]);
+      if (v > best_v) { best_v = v; best = k; }
+    }
+  }
+  const int id = lut ? lut[best] : best;
+  if (out_u8) out_u8[i] = (unsigned char)id;
+  if (out_i64) out_i64[i] = id;
+}
+}  // namespace ew
+
+int ew_ingest_rgb8(const unsigned char* src, float* dst, int h, int w, const float* mean, const float* stdv, cudaStream_t s) {
+  B200_REQUIRE(h > 0 && w > 0 && mean && stdv, "ingest_rgb8: bad arguments");
+  const long long hw = (long long)h * w;
+  ew::ingest_rgb8_kernel<<<(unsigned)ceil_div(hw, 256ll), 256, 0, s>>>(src, dst, hw, mean[0], mean[1], mean[2], stdv[0],
+                                                                      stdv[1], stdv[2]);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_prob_to_ids(const float* prob, int c, int h, int w, int out_h, int out_w, int flip, const int* lut,
+                   unsigned char* out_u8, long long* out_i64, cudaStream_t s) {
+  B200_REQUIRE(c >= 1 && h > 0 && w > 0 && out_h > 0 && out_w > 0 && (out_u8 || out_i64), "prob_to_ids: bad arguments");
+  const long long n = (long long)out_h * out_w;
+  ew::prob_to_ids_kernel<<<(unsigned)ceil_div(n, 256ll), 256, 0, s>>>(prob, c, h, w, out_h, out_w, flip, (float)h / out_h,
+                                                                     (float)w / out_w, lut, out_u8, out_i64);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
 int ew_transpose_append(const __half* src, __half* dst, long long ld_dst, int n, int C, cudaStream_t s) {
   ew::transpose_append_kernel<<<dim3(ceil_div(n, 32), ceil_div(C, 32)), 256, 0, s>>>(src, dst, ld_dst, n, C);
   B200_LAUNCH_CHECK();

@@ -76,6 +76,10 @@ _SIGNATURES = {
     'deva_b200_output_tail': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'deva_b200_head_gather3x3': (c_int, [c_void_p, c_void_p, ctypes.c_float, c_int, c_int, c_int, c_void_p]),
     'deva_b200_transpose_append': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    'deva_b200_ingest_rgb8': (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(ctypes.c_float),
+                                      ctypes.POINTER(ctypes.c_float), c_void_p]),
+    'deva_b200_prob_to_ids': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES.keys())
 
@@ -271,6 +275,17 @@ def key_tail(y, ld, q, ck, key, shrinkage, selection):
 def output_tail(logits, agg, prob, logits_out, k, h, w):
     _check(lib().deva_b200_output_tail(_ptr(logits), _ptr(agg), _ptr(prob), _ptr(logits_out), k, h, w, _stream()),
            'output_tail')
+
+
+def ingest_rgb8(src, dst, h, w, mean, std):
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _check(lib().deva_b200_ingest_rgb8(_ptr(src), _ptr(dst), h, w, m, s, _stream()), 'ingest_rgb8')
+
+
+def prob_to_ids(prob, c, h, w, out_h, out_w, flip, lut, out_u8, out_i64):
+    _check(lib().deva_b200_prob_to_ids(_ptr(prob), c, h, w, out_h, out_w, int(flip), _p(lut), _p(out_u8), _p(out_i64),
+                                       _stream()), 'prob_to_ids')
 
 
 def transpose_append(src, dst, ld_dst, n, c):
