@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DEVA_B200_ABI_VERSION 7
+#define DEVA_B200_ABI_VERSION 8
 #define DEVA_B200_LIST_PITCH 32 /* row pitch of top-k outputs == max supported top_k */
 #define DEVA_B200_MAX_GROUPS 256 /* objects per deva_b200_readout call */
 
@@ -123,6 +123,28 @@ DEVA_B200_API int deva_b200_readout_sparse(const void* values, int64_t values_ld
                                            int rows_per_group, const int32_t* idx, const float* w, int top_k,
                                            int n_window, int q, void* workspace, float* out, int64_t ld_out,
                                            void* out_tok, deva_stream_t stream);
+/* Bank-sharded read (one video, slots split over the ranks of an NVLink box): readout GEMM fused with the
+ * reduce-scatter by object.  Each rank multiplies ITS slots; the tile of group g is added (red.add.f32, system scope)
+ * straight from the GEMM epilogue into rank_dst[owner[g]] + out_row[g] * ld_out, the fp32 [objects_owned * cv, q]
+ * buffer of the rank that owns object g - peer memory mapped through CUDA IPC, or local.  rank_dst: HOST array of
+ * n_ranks (<= 8) device pointers.  The caller zeroes the buffers beforehand and fences the ranks afterwards. */
+DEVA_B200_API int deva_b200_readout_sparse_scatter(const void* values, int64_t values_ld, int64_t values_rows,
+                                                   const int32_t* val_row, const int32_t* out_row,
+                                                   const int32_t* owner, int n_groups, int rows_per_group,
+                                                   const int32_t* idx, const float* w, int top_k, int n_window, int q,
+                                                   void* workspace, float* const* rank_dst, int n_ranks,
+                                                   int64_t ld_out, deva_stream_t stream);
+/* Let kernels launched on `device` dereference memory of `peer_device` (cudaDeviceEnablePeerAccess; already-enabled
+ * is not an error).  Needed once per peer before deva_b200_readout_sparse_scatter is given IPC-mapped pointers. */
+DEVA_B200_API int deva_b200_enable_peer_access(int device, int peer_device);
+/* Peer-visible buffers for the scatter read-out.  peer_alloc: cudaMalloc (zeroed) on `device` + its 64-byte CUDA IPC
+ * handle, to be sent to the other ranks; peer_open: map a peer's handle INTO `device`'s address space
+ * (cudaIpcOpenMemHandle with lazy peer access - an IPC mapping opened under the exporter's device is not reachable
+ * from other devices); peer_close / peer_free undo them. */
+DEVA_B200_API int deva_b200_peer_alloc(int device, int64_t bytes, void** ptr, uint8_t handle[64]);
+DEVA_B200_API int deva_b200_peer_open(int device, const uint8_t handle[64], void** ptr);
+DEVA_B200_API int deva_b200_peer_close(int device, void* ptr);
+DEVA_B200_API int deva_b200_peer_free(int device, void* ptr);
 
 /* ---- bank compaction (sieve_by_range / remove_obsolete_features, kv_memory_store.py:127-185) ----------
  * dst must not alias src.  idx: device int32 [n]. */

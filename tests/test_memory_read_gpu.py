@@ -238,3 +238,27 @@ def test_sharded_reader_single_rank_matches_oracle():
         total += part.cpu()
     torch.cuda.synchronize()
     assert float((total - out).abs().max()) < 1e-5 * max(1.0, float(out.abs().max()))
+
+
+def test_scatter_readout_single_rank():
+    """Fused readout + reduce-scatter by object, degenerate case of one rank: the red.add epilogue into the (local)
+    owner buffer reproduces the stored readout; two reads in a row do not accumulate."""
+    from deva import _native
+    from deva.inference.sharded_memory import ShardedBankReader
+    _native.require_device()
+    dev = torch.device('cuda', 0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    ck, cv, k, n, q = 64, 512, 3, 3000, 1000
+    mk = torch.randn(ck, n, device=dev, generator=g)
+    ms = 1 + torch.rand(n, device=dev, generator=g)
+    mv = torch.randn(k * cv, n, device=dev, generator=g)
+    qk = torch.randn(ck, q, device=dev, generator=g)
+    qe = torch.sigmoid(torch.randn(ck, q, device=dev, generator=g))
+    rd = ShardedBankReader(ck, cv, k, n, 0, dev)
+    rd.load(mk, ms, mv)
+    want = rd.read(qk, qe, count_usage=False)
+    for _ in range(2):
+        got = rd.read_scatter(qk, qe, count_usage=False)
+        torch.cuda.synchronize()
+        assert got.shape == want.shape
+        assert float((got - want).abs().max()) < 1e-5 * float(want.abs().max()) + 1e-6

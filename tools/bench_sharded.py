@@ -20,6 +20,8 @@ def main():
     ap.add_argument('--objects', dest='k', type=int, default=32)
     ap.add_argument('--check', action='store_true', help='compare with the unsharded read on rank 0 (needs the memory)')
     ap.add_argument('--iters', type=int, default=10)
+    ap.add_argument('--scatter', action='store_true', help='also run the fused readout + reduce-scatter-by-object '
+                    '(peer-memory red.add from the GEMM epilogue) and compare it with the all-reduce read')
     a = ap.parse_args()
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
@@ -54,6 +56,25 @@ def main():
         res['max_abs_diff_vs_unsharded'] = float((out - want).abs().max())
         res['scale'] = float(want.abs().max())
         del ref, want
+    if a.scatter:
+        own = rd.read_scatter(qk, qe, count_usage=False).clone()
+        olo, ohi = rd.objects_of(rank)
+        diff = (own - out[olo * CV:ohi * CV]).abs().max() if ohi > olo else torch.zeros((), device=dev)
+        if world > 1:
+            dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        res['scatter_max_abs_diff_vs_allreduce'] = float(diff)
+        tss = []
+        for _ in range(a.iters):
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); rd.read_scatter(qk, qe, count_usage=False); e1.record(); torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tss.append(float(t))
+        tss.sort()
+        res['ms_scatter'] = tss[len(tss) // 2]
     ts = []
     for _ in range(a.iters):
         if world > 1:

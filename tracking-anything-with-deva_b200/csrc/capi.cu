@@ -4,6 +4,8 @@
 #include <cuda_fp16.h>
 
 #include "bank_ops.h"
+#include <string.h>
+
 #include "common.h"
 #include "conv.h"
 #include "elementwise.h"
@@ -84,6 +86,63 @@ DEVA_B200_API int deva_b200_readout_sparse(const void* values, int64_t values_ld
                                            void* out_tok, deva_stream_t stream) {
   return launch_readout_sparse(H(values), values_ld, values_rows, val_row, out_row, n_groups, rows_per_group, idx, w,
                                top_k, n_window, q, workspace, out, ld_out, H(out_tok), S(stream));
+}
+DEVA_B200_API int deva_b200_readout_sparse_scatter(const void* values, int64_t values_ld, int64_t values_rows,
+                                                   const int32_t* val_row, const int32_t* out_row,
+                                                   const int32_t* owner, int n_groups, int rows_per_group,
+                                                   const int32_t* idx, const float* w, int top_k, int n_window, int q,
+                                                   void* workspace, float* const* rank_dst, int n_ranks,
+                                                   int64_t ld_out, deva_stream_t stream) {
+  return launch_readout_sparse(H(values), values_ld, values_rows, val_row, out_row, n_groups, rows_per_group, idx, w,
+                               top_k, n_window, q, workspace, nullptr, ld_out, nullptr, S(stream), owner, rank_dst, n_ranks);
+}
+DEVA_B200_API int deva_b200_enable_peer_access(int device, int peer_device) {
+  int prev = 0, can = 0;
+  B200_CUDA(cudaGetDevice(&prev));
+  B200_CUDA(cudaDeviceCanAccessPeer(&can, device, peer_device));
+  B200_REQUIRE(can, "device %d has no peer-to-peer path to device %d", device, peer_device);
+  B200_CUDA(cudaSetDevice(device));
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
+  (void)cudaSetDevice(prev);
+  B200_CUDA(e);
+  return 0;
+}
+namespace {
+struct DeviceScope {
+  int prev = 0;
+  explicit DeviceScope(int d) { cudaGetDevice(&prev); cudaSetDevice(d); }
+  ~DeviceScope() { cudaSetDevice(prev); }
+};
+}  // namespace
+DEVA_B200_API int deva_b200_peer_alloc(int device, int64_t bytes, void** ptr, uint8_t handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  B200_REQUIRE(bytes > 0 && ptr && handle, "peer_alloc: bad arguments");
+  DeviceScope scope(device);
+  B200_CUDA(cudaMalloc(ptr, (size_t)bytes));
+  B200_CUDA(cudaMemset(*ptr, 0, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  B200_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+  memcpy(handle, &h, 64);
+  return 0;
+}
+DEVA_B200_API int deva_b200_peer_open(int device, const uint8_t handle[64], void** ptr) {
+  B200_REQUIRE(ptr && handle, "peer_open: bad arguments");
+  DeviceScope scope(device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  B200_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+DEVA_B200_API int deva_b200_peer_close(int device, void* ptr) {
+  DeviceScope scope(device);
+  B200_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+DEVA_B200_API int deva_b200_peer_free(int device, void* ptr) {
+  DeviceScope scope(device);
+  B200_CUDA(cudaFree(ptr));
+  return 0;
 }
 DEVA_B200_API int deva_b200_gather_rows(void* dst, const void* src, const int32_t* idx, int n, int row_bytes, deva_stream_t stream) {
   return launch_gather_rows(dst, src, idx, n, row_bytes, S(stream));

@@ -11,6 +11,8 @@
 // together share value panels and affinity panels in L2.
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 #include "readout.h"
@@ -248,7 +250,17 @@ struct SpParams {
   const uint32_t* entries;   // [n_tiles][BN * kListCapR]
   int val_row[kMaxGroups];
   int out_row[kMaxGroups];
+  // scatter-reduce mode (bank-sharded read): group g's tile is ADDED (red.add over NVLink / locally) into the buffer
+  // of the rank that owns the object, rank_dst[owner[g]] + out_row[g] * ldo, instead of stored to `out`
+  float* rank_dst[kMaxPeers];
+  unsigned char owner[kMaxGroups];
+  int reduce;
 };
+
+__device__ __forceinline__ void red_add_v4_sys(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
 
 __global__ void __launch_bounds__(SP_THREADS, 1)
 readout_sparse_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ SpParams p) {
@@ -383,7 +395,7 @@ readout_sparse_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_co
       tile_coords(tile, p.m_tiles, p.n_tiles, m, n);
       const int g = m / p.tiles_per_group;
       const long long R = p.out_row[g] + (long long)(m - g * p.tiles_per_group) * BM + row;
-      float* dst = p.out + R * p.ldo;
+      float* dst = (p.reduce ? p.rank_dst[p.owner[g]] : p.out) + R * p.ldo;
       const long long obj = R / p.rows_per_group;
       const int ch = (int)(R - obj * p.rows_per_group);
       __half* dt = p.out_tok ? p.out_tok + (obj * p.q) * p.rows_per_group + ch : nullptr;
@@ -396,7 +408,18 @@ readout_sparse_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_co
         tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + c * 32, r);
         tmem_ld_wait();
         const int q0 = n * BN + c * 32;
-        if (dt) {
+        if (p.reduce) {  // partial sums of this rank's slots -> the owner's buffer (peer memory or local)
+          if (p.reduce == 1 && q0 + 32 <= p.q && p.ldo % 4 == 0) {  // 16-byte vector reductions
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4_sys(dst + q0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                             __uint_as_float(r[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (q0 + j < p.q) atomicAdd_system(dst + q0 + j, __uint_as_float(r[j]));
+          }
+        } else if (dt) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (q0 + j < p.q) dt[(long long)(q0 + j) * p.rows_per_group] = __float2half_rn(__uint_as_float(r[j]));
@@ -482,8 +505,10 @@ size_t readout_sparse_workspace_bytes(int q, int n_window) {
 int launch_readout_sparse(const __half* values, long long values_ld, long long values_rows, const int* val_row,
                           const int* out_row, int n_groups, int rows_per_group, const int* idx, const float* w,
                           int top_k, int n_window, int q, void* workspace, float* out, long long ldo, __half* out_tok,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const int* owner, float* const* rank_dst, int n_ranks) {
   using namespace readout;
+  B200_REQUIRE(!rank_dst || (owner && n_ranks >= 1 && n_ranks <= kMaxPeers && !out_tok),
+               "readout: scatter-reduce needs owners and 1..%d destination ranks", kMaxPeers);
   B200_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups, "readout: n_groups %d out of range [1,%d]", n_groups, kMaxGroups);
   B200_REQUIRE(rows_per_group % BM == 0, "readout: rows_per_group %d must be a multiple of %d", rows_per_group, BM);
   B200_REQUIRE(n_window >= 1 && q >= 1 && top_k >= 1 && top_k <= kListCapR, "readout: bad shape");
@@ -504,6 +529,16 @@ int launch_readout_sparse(const __half* values, long long values_ld, long long v
   uint32_t* entries = reinterpret_cast<uint32_t*>(offsets + (size_t)p.n_tiles * (p.k_blocks + 1));
   p.offsets = offsets; p.entries = entries;
   for (int i = 0; i < n_groups; ++i) { p.val_row[i] = val_row[i]; p.out_row[i] = out_row[i]; }
+  // DEVA_B200_SCATTER_RED=scalar: one 4-byte reduction per element instead of red.add.v4 (debugging aid)
+  static const bool scalar_red = [] { const char* e = getenv("DEVA_B200_SCATTER_RED"); return e && e[0] == 's'; }();
+  p.reduce = rank_dst ? (scalar_red ? 2 : 1) : 0;
+  if (rank_dst) {
+    for (int r = 0; r < n_ranks; ++r) p.rank_dst[r] = rank_dst[r];
+    for (int i = 0; i < n_groups; ++i) {
+      B200_REQUIRE(owner[i] >= 0 && owner[i] < n_ranks, "readout: owner %d out of range", owner[i]);
+      p.owner[i] = (unsigned char)owner[i];
+    }
+  }
   B200_REQUIRE((size_t)(p.k_blocks + 1) * 4 <= 200 * 1024, "readout: window of %d slots too large for the bucket pass", n_window);
   static bool configured = false;
   if (!configured) {

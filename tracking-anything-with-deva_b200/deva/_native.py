@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libdeva_b200.so')
-ABI_VERSION = 7
+ABI_VERSION = 8
 LIST_PITCH = 32
 MAX_GROUPS = 256
 
@@ -57,6 +57,14 @@ _SIGNATURES = {
     'deva_b200_readout_sparse': (c_int, [c_void_p, c_int64, c_int64, POINTER(c_int32), POINTER(c_int32), c_int, c_int,
                                          c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p,
                                          c_void_p]),
+    'deva_b200_readout_sparse_scatter': (c_int, [c_void_p, c_int64, c_int64, POINTER(c_int32), POINTER(c_int32),
+                                                 POINTER(c_int32), c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                                 c_void_p, POINTER(c_void_p), c_int, c_int64, c_void_p]),
+    'deva_b200_enable_peer_access': (c_int, [c_int, c_int]),
+    'deva_b200_peer_alloc': (c_int, [c_int, c_int64, POINTER(c_void_p), c_char_p]),
+    'deva_b200_peer_open': (c_int, [c_int, c_char_p, POINTER(c_void_p)]),
+    'deva_b200_peer_close': (c_int, [c_int, c_void_p]),
+    'deva_b200_peer_free': (c_int, [c_int, c_void_p]),
     'deva_b200_gather_rows': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'deva_b200_gather_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'deva_b200_gather_cols_f16': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
@@ -196,6 +204,43 @@ def readout_sparse(values, values_ld, values_rows, val_row, out_row, rows_per_gr
     _check(lib().deva_b200_readout_sparse(_ptr(values), values_ld, values_rows, arr_v, arr_o, n, rows_per_group,
                                           _ptr(idx), _ptr(w), top_k, n_window, q, _ptr(workspace), _ptr(out), ld_out,
                                           _ptr(out_tok), _stream()), 'readout_sparse')
+
+
+def readout_sparse_scatter(values, values_ld, values_rows, val_row, out_row, owner, rows_per_group, idx, w, top_k,
+                           n_window, q, workspace, rank_dst_ptrs, ld_out):
+    """rank_dst_ptrs: device addresses (ints) of every rank's fp32 [objects_owned * rows_per_group, q] buffer."""
+    n = len(val_row)
+    arr_v, arr_o, arr_w = (c_int32 * n)(*val_row), (c_int32 * n)(*out_row), (c_int32 * n)(*owner)
+    ptrs = (c_void_p * len(rank_dst_ptrs))(*rank_dst_ptrs)
+    _check(lib().deva_b200_readout_sparse_scatter(_ptr(values), values_ld, values_rows, arr_v, arr_o, arr_w, n,
+                                                  rows_per_group, _ptr(idx), _ptr(w), top_k, n_window, q,
+                                                  _ptr(workspace), ptrs, len(rank_dst_ptrs), ld_out, _stream()),
+           'readout_sparse_scatter')
+
+
+def peer_alloc(device: int, nbytes: int):
+    """-> (device address, 64-byte CUDA IPC handle) of a zeroed cudaMalloc'ed buffer on ``device``."""
+    ptr, handle = c_void_p(), ctypes.create_string_buffer(64)
+    _check(lib().deva_b200_peer_alloc(device, nbytes, ctypes.byref(ptr), handle), 'peer_alloc')
+    return int(ptr.value), handle.raw
+
+
+def peer_open(device: int, handle: bytes) -> int:
+    ptr = c_void_p()
+    _check(lib().deva_b200_peer_open(device, handle, ctypes.byref(ptr)), 'peer_open')
+    return int(ptr.value)
+
+
+def peer_close(device: int, ptr: int):
+    _check(lib().deva_b200_peer_close(device, c_void_p(ptr)), 'peer_close')
+
+
+def peer_free(device: int, ptr: int):
+    _check(lib().deva_b200_peer_free(device, c_void_p(ptr)), 'peer_free')
+
+
+def enable_peer_access(device: int, peer_device: int):
+    _check(lib().deva_b200_enable_peer_access(device, peer_device), 'enable_peer_access')
 
 
 def gather_rows(dst, src, idx, n, row_bytes):
