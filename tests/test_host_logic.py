@@ -128,6 +128,43 @@ def test_match_and_merge_matches_reference_logic():
         assert om.find_object_by_id(11).poke_count == 1
 
 
+def test_pad_unpad_roundtrip_property():
+    """pad_divide_by / unpad (tensor_utils.py:7-48) for arbitrary sizes: multiple of d, symmetric with the odd pixel at
+    the bottom/right, zero filled, exact round trip - and identical to the oracle."""
+    from hypothesis import given, settings, strategies as st
+    from deva.utils.tensor_utils import pad_divide_by, unpad
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 70), st.integers(1, 70), st.sampled_from([8, 16, 32]))
+    def check(h, w, d):
+        x = torch.arange(2 * h * w, dtype=torch.float32).view(2, h, w) + 1
+        y, pad = pad_divide_by(x, d)
+        assert y.shape[-2] % d == 0 and y.shape[-1] % d == 0 and y.shape[-2] - h < d and y.shape[-1] - w < d
+        lw, uw, lh, uh = pad
+        assert 0 <= uw - lw <= 1 and 0 <= uh - lh <= 1
+        assert float(y.double().sum()) == float(x.double().sum())  # padding is zeros
+        assert torch.equal(unpad(y, pad), x)
+        ref, rpad = pad_to_multiple(x, d)
+        assert tuple(pad) == tuple(rpad) and torch.equal(y, ref)
+
+    check()
+
+
+def test_id_lut_matches_tmp_to_obj_cls():
+    """frame_io.id_lut is the table form of ObjectManager.tmp_to_obj_cls (object_manager.py:112-117)."""
+    from deva.inference.frame_io import id_lut
+    from deva.inference.object_manager import ObjectManager
+    np.random.seed(3)
+    om = ObjectManager()
+    om.add_new_objects([4, 9, 250, 7])
+    om.delete_object([9])
+    lut = id_lut(om, 6, 'cpu')
+    mask = torch.randint(0, 4, (5, 7))
+    assert lut.dtype == torch.int32 and lut[0] == 0
+    assert torch.equal(lut[mask].long(), om.tmp_to_obj_cls(mask))
+    assert lut.tolist()[len(om.tmp_id_to_obj) + 1:] == [0] * (6 - len(om.tmp_id_to_obj) - 1)
+
+
 def test_consensus_selection_is_optimal():
     """solve_exact (no ILP solver needed) == exhaustive enumeration of the reference's integer program
     (consensus_automatic.py:28-79) on random conflict graphs, including the tie-breaking rule."""
