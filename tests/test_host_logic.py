@@ -165,6 +165,31 @@ def test_id_lut_matches_tmp_to_obj_cls():
     assert lut.tolist()[len(om.tmp_id_to_obj) + 1:] == [0] * (6 - len(om.tmp_id_to_obj) - 1)
 
 
+def test_package_chains_to_reference_checkout(tmp_path):
+    """SURVEY 8(b) "imports that must resolve": with this package first on sys.path and a reference checkout after it,
+    modules we provide load from here, everything else (dataset readers, deva.ext, ...) from the checkout."""
+    import subprocess
+    import sys
+    import textwrap
+    for d in ('deva', 'deva/inference', 'deva/inference/data', 'deva/ext', 'deva/utils'):
+        (tmp_path / d).mkdir(parents=True, exist_ok=True)
+        (tmp_path / d / '__init__.py').write_text('')
+    (tmp_path / 'deva/inference/data/fake_reader.py').write_text(
+        'from deva.inference.object_info import ObjectInfo\nKIND = "reference reader"\n')
+    (tmp_path / 'deva/inference/object_info.py').write_text('raise RuntimeError("shadowed module must not load")\n')
+    (tmp_path / 'deva/utils/pano_utils.py').write_text('def id_to_rgb(i): return (i, 0, 0)\n')
+    pkg = os.path.join(ROOT, 'tracking-anything-with-deva_b200')
+    code = textwrap.dedent("""
+        import deva.inference.data.fake_reader as r, deva.inference.object_info as oi, deva.utils.pano_utils as pu, deva.ext
+        print(r.KIND, '|', oi.__file__, '|', pu.id_to_rgb(3), '|', r.ObjectInfo is oi.ObjectInfo)
+    """)
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True,
+                         env=dict(os.environ, PYTHONPATH=pkg + os.pathsep + str(tmp_path)))
+    assert out.returncode == 0, out.stderr
+    kind, oi_file, rgb, same = [t.strip() for t in out.stdout.strip().split('|')]
+    assert kind == 'reference reader' and oi_file.startswith(pkg) and rgb == '(3, 0, 0)' and same == 'True'
+
+
 def test_consensus_selection_is_optimal():
     """solve_exact (no ILP solver needed) == exhaustive enumeration of the reference's integer program
     (consensus_automatic.py:28-79) on random conflict graphs, including the tie-breaking rule."""
