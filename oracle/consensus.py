@@ -10,7 +10,7 @@ reference's `pulp` solver is absent from the image; the minting script plugs the
 reference's `solve_with_pulp` hook, which the reference itself documents as a replaceable fallback solver).
 """
 from collections import defaultdict
-from typing import Callable, Dict, List, Optional, Tuple
+from typing import Callable, List, Tuple
 
 import numpy as np
 import torch

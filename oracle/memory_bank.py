@@ -6,7 +6,7 @@ object group instead of five parallel dicts.  Tensors stay channel-major fp32 an
 concatenation exactly like the reference, so sizes, ordering and usage counters can be
 compared slot by slot.
 """
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional
 
 import torch

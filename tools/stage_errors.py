@@ -1,7 +1,6 @@
 """Where does the native (fp16-operand) conv stack lose accuracy?  Runs each network stage of the golden clip's first
 frames through the hand-written kernels and through the cuDNN-fp32 debug engine ON THE SAME INPUTS and prints the
 max-abs / relative error per stage output (single step, no recurrence).  GPU only."""
-import json
 import os
 import sys
 

@@ -6,7 +6,7 @@ but every pixel count comes from ONE joint label histogram (one device reduction
 instead of a ``.sum()`` per mask pair.  Integer logic; identical results.
 """
 import warnings
-from typing import Dict, List, Literal, Optional, Tuple
+from typing import Dict, List, Literal, Tuple
 
 import torch
 

@@ -17,7 +17,7 @@ stack while the hand-written NHWC tcgen05 implicit-GEMM kernels land layer by la
 on the device, never a CPU path.  The memory read never goes through a backend - it is always the
 sm_100a kernels in deva/inference/memory_manager.py.
 """
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 import torch.nn.functional as F

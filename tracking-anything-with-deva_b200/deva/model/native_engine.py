@@ -11,13 +11,13 @@ Tensors crossing the public API keep the reference's [B, C, H, W] / [1, K, C, h,
 permuted views of NHWC fp16 storage, so they flow through ``DEVAInferenceCore`` / ``MemoryManager``
 without conversion.
 """
-from typing import Dict, Optional, Tuple
+from typing import Dict, Tuple
 
 import torch
 
 from deva import _native as nat
 from deva.model import native_ops as ops
-from deva.model.engine import ConvSpec, LayerTable
+from deva.model.engine import LayerTable
 
 
 def _to_nhwc(t: torch.Tensor) -> torch.Tensor:
