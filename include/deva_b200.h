@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DEVA_B200_ABI_VERSION 8
+#define DEVA_B200_ABI_VERSION 9
 #define DEVA_B200_LIST_PITCH 32 /* row pitch of top-k outputs == max supported top_k */
 #define DEVA_B200_MAX_GROUPS 256 /* objects per deva_b200_readout call */
 
@@ -216,6 +216,13 @@ DEVA_B200_API int deva_b200_area_down_plane(const float* x, float* y, int b, int
 DEVA_B200_API int deva_b200_cbam(const void* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                  const float* ws, const float* bs, float* scratch, void* raw, void* relu, int b, int h,
                                  int w, int c, int r, deva_stream_t stream);
+/* Split-precision twins for a residual stream carried as fp16 (hi, lo) pairs (opt-in, DEVA_B200_RESIDUAL_LO=1): the
+ * input is g + g_lo (x + x_lo), the raw result is written as (raw, raw_lo), the ReLU'd copy (an MMA operand) as hi. */
+DEVA_B200_API int deva_b200_up2_add_split(const void* g, const void* g_lo, const void* skip, void* raw, void* raw_lo,
+                                          void* relu, int b, int h, int w, int c, deva_stream_t stream);
+DEVA_B200_API int deva_b200_cbam_split(const void* x, const void* x_lo, const float* w1, const float* b1, const float* w2,
+                                       const float* b2, const float* ws, const float* bs, float* scratch, void* raw,
+                                       void* raw_lo, void* relu, int b, int h, int w, int c, int r, deva_stream_t stream);
 /* sensory GRU gates (modules.py:145-149): values fp16 [pixels, 3c], h fp16 [pixels, c] -> out fp16 */
 DEVA_B200_API int deva_b200_gru(const void* values, const void* h, void* out, int64_t pixels, int c,
                                 deva_stream_t stream);

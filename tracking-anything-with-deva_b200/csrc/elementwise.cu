@@ -184,6 +184,68 @@ up2_add_kernel(const __half* __restrict__ g, const __half* __restrict__ skip, __
   }
 }
 
+// Split-precision twin (residual stream carried as fp16 hi/lo pairs, DESIGN section 4 "precision plan"): g = g + g_lo on
+// input; the raw sum is written as (hi, lo), the ReLU'd copy - an MMA operand only - as hi.
+__device__ __forceinline__ void st8_split(__half* hi, __half* lo, const float (&f)[8]) {
+  uint4 vh, vl;
+  __half2* h2 = reinterpret_cast<__half2*>(&vh);
+  __half2* l2 = reinterpret_cast<__half2*>(&vl);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h2[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+    const float2 back = __half22float2(h2[e]);
+    l2[e] = __floats2half2_rn(f[2 * e] - back.x, f[2 * e + 1] - back.y);
+  }
+  *reinterpret_cast<uint4*>(hi) = vh;
+  *reinterpret_cast<uint4*>(lo) = vl;
+}
+__global__ void __launch_bounds__(256)
+up2_add_split_kernel(const __half* __restrict__ g, const __half* __restrict__ g_lo, const __half* __restrict__ skip,
+                     __half* __restrict__ raw, __half* __restrict__ raw_lo, __half* __restrict__ relu, int B, int h, int w,
+                     int C) {
+  const int H = 2 * h, W = 2 * w, C8 = C / 8;
+  const int b = blockIdx.y / H, Y = blockIdx.y - b * H;
+  const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.f);
+  const int y0 = (int)sy, y1 = min(y0 + 1, h - 1);
+  const float wy = sy - y0;
+  const long long o0 = ((long long)b * h + y0) * w * C, o1 = ((long long)b * h + y1) * w * C;
+  const __half* sk = skip + (long long)Y * W * C;
+  const long long obase = ((long long)b * H + Y) * W * C;
+  const int row_vecs = W * C8;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < row_vecs; i += gridDim.x * 256) {
+    const int X = i / C8, c = (i - X * C8) * 8;
+    const float sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.f);
+    const int x0 = (int)sx, x1 = min(x0 + 1, w - 1);
+    const float wx = sx - x0;
+    float a[8], bq[8], cq[8], d[8], l[8], o[8], s_[8];
+    ld8(g + o0 + x0 * C + c, a);
+    ld8(g + o0 + x1 * C + c, bq);
+    ld8(g + o1 + x0 * C + c, cq);
+    ld8(g + o1 + x1 * C + c, d);
+    ld8(g_lo + o0 + x0 * C + c, l);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] += l[e];
+    ld8(g_lo + o0 + x1 * C + c, l);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) bq[e] += l[e];
+    ld8(g_lo + o1 + x0 * C + c, l);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cq[e] += l[e];
+    ld8(g_lo + o1 + x1 * C + c, l);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] += l[e];
+    ld8(sk + X * C + c, s_);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float top = a[e] + (bq[e] - a[e]) * wx, bot = cq[e] + (d[e] - cq[e]) * wx;
+      o[e] = top + (bot - top) * wy + s_[e];
+    }
+    const long long off = obase + X * C + c;
+    st8_split(raw + off, raw_lo + off, o);
+    if (relu) st8(relu + off, o, true);
+  }
+}
+
 // r x r average pooling (F.interpolate mode='area' with an integer ratio), NHWC fp16
 __global__ void area_down_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C, int r) {
   const int Ho = H / r, Wo = W / r, C8 = C / 8;
@@ -323,6 +385,37 @@ __global__ void cbam_apply_kernel(const __half* __restrict__ x, const float* __r
     const float v = __half2float(x[pix * C + c]);
     const float o = v + v * g[c] * sg;
     if (raw) raw[pix * C + c] = __float2half_rn(o);
+    if (relu) relu[pix * C + c] = __float2half_rn(fmaxf(o, 0.f));
+  }
+}
+
+// split-precision twin of cbam_apply_kernel: x = x + x_lo on input, raw written as (hi, lo), relu as hi
+__global__ void cbam_apply_split_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo,
+                                        const float* __restrict__ gate, const float* __restrict__ stats,
+                                        const float* __restrict__ ws, const float* __restrict__ bs,
+                                        __half* __restrict__ raw, __half* __restrict__ raw_lo, __half* __restrict__ relu,
+                                        int B, int H, int W, int C) {
+  const long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pix >= (long long)B * H * W) return;
+  const int b = (int)(pix / ((long long)H * W));
+  const int rem = (int)(pix - (long long)b * H * W);
+  const int y = rem / W, xq = rem - y * W;
+  float a = 0.f;
+  for (int t = lane; t < 98; t += 32) {
+    const int ch = t / 49, k = t % 49, dy = k / 7 - 3, dx = k % 7 - 3;
+    const int yy = y + dy, xx = xq + dx;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) a += ws[t] * stats[(((long long)b * H + yy) * W + xx) * 2 + ch];
+  }
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  const float sg = sigmoidf_(a + bs[0]);
+  const float* g = gate + b * C;
+  for (int c = lane; c < C; c += 32) {
+    const float v = __half2float(x[pix * C + c]) + __half2float(x_lo[pix * C + c]);
+    const float o = v + v * g[c] * sg;
+    const __half hi = __float2half_rn(o);
+    raw[pix * C + c] = hi;
+    raw_lo[pix * C + c] = __float2half_rn(o - __half2float(hi));
     if (relu) relu[pix * C + c] = __float2half_rn(fmaxf(o, 0.f));
   }
 }
@@ -485,6 +578,14 @@ int ew_up2_add(const __half* g, const __half* skip, __half* raw, __half* relu, i
   B200_LAUNCH_CHECK();
   return 0;
 }
+int ew_up2_add_split(const __half* g, const __half* g_lo, const __half* skip, __half* raw, __half* raw_lo, __half* relu,
+                     int B, int h, int w, int C, cudaStream_t s) {
+  B200_REQUIRE(C % 8 == 0 && g_lo && raw && raw_lo, "up2_add_split: C %% 8 and the hi/lo tensors are required");
+  ew::up2_add_split_kernel<<<dim3(ceil_div(2 * w * (C / 8), 256 * 2), B * 2 * h), 256, 0, s>>>(g, g_lo, skip, raw, raw_lo,
+                                                                                              relu, B, h, w, C);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
 int ew_area_down(const __half* x, __half* y, int B, int H, int W, int C, int r, cudaStream_t s) {
   B200_REQUIRE(C % 8 == 0 && H % r == 0 && W % r == 0, "area_down: shape");
   ew::area_down_kernel<<<grid_of((long long)B * (H / r) * (W / r) * (C / 8)), 256, 0, s>>>(x, y, B, H, W, C, r);
@@ -514,6 +615,28 @@ int ew_cbam(const __half* x, const float* w1, const float* b1, const float* w2, 
   ew::cbam_stats_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, gate, stats, B, HW, C);
   B200_LAUNCH_CHECK();
   ew::cbam_apply_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, gate, stats, ws, bs, raw, relu, B, H, W, C);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_cbam_split(const __half* x, const __half* x_lo, const float* w1, const float* b1, const float* w2, const float* b2,
+                  const float* ws, const float* bs, float* scratch, __half* raw, __half* raw_lo, __half* relu, int B, int H,
+                  int W, int C, int R, cudaStream_t s) {
+  // the gates (channel MLP, 7x7 spatial conv) are sigmoids of pooled statistics: the hi part of x is enough for them
+  B200_REQUIRE(x_lo && raw && raw_lo, "cbam_split: the hi/lo tensors are required");
+  float* psum = scratch;
+  float* pmax = psum + (long long)B * ew::kPoolSplit * C;
+  float* gate = pmax + (long long)B * ew::kPoolSplit * C;
+  float* stats = gate + (long long)B * C;
+  const int HW = H * W;
+  ew::cbam_pool_kernel<<<dim3(ceil_div(C, 128), B, ew::kPoolSplit), 128, 0, s>>>(x, psum, pmax, HW, C);
+  B200_LAUNCH_CHECK();
+  ew::cbam_mlp_kernel<<<B, 256, (2 * C + 2 * R) * sizeof(float), s>>>(psum, pmax, HW, w1, b1, w2, b2, gate, C, R);
+  B200_LAUNCH_CHECK();
+  const long long warps = (long long)B * HW;
+  ew::cbam_stats_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, gate, stats, B, HW, C);
+  B200_LAUNCH_CHECK();
+  ew::cbam_apply_split_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, x_lo, gate, stats, ws, bs, raw, raw_lo, relu, B,
+                                                                        H, W, C);
   B200_LAUNCH_CHECK();
   return 0;
 }

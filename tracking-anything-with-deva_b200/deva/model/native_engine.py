@@ -11,6 +11,7 @@ Tensors crossing the public API keep the reference's [B, C, H, W] / [1, K, C, h,
 permuted views of NHWC fp16 storage, so they flow through ``DEVAInferenceCore`` / ``MemoryManager``
 without conversion.
 """
+import os
 from typing import Dict, Tuple
 
 import torch
@@ -41,6 +42,10 @@ class NativeEngine:
     prefers_nhwc = True
 
     def __init__(self, sd: Dict[str, torch.Tensor]):
+        # DEVA_B200_RESIDUAL_LO=1 (opt-in, see DESIGN "precision plan"): the decoder's residual / skip stream - block
+        # outputs, CBAM residual, bilinear x2 + skip - travels as fp16 (hi, lo) pairs instead of being rounded to fp16 at
+        # every block; MMA operands stay single fp16.  Emulated gain on the golden clip: 1.98e-3 -> 1.17e-3 max |dprob|.
+        self.residual_lo = os.environ.get('DEVA_B200_RESIDUAL_LO', '0') == '1'
         t = LayerTable(sd)
         self.key_dim, self.value_dim = t.key_dim, t.value_dim
         self.device = next(iter(sd.values())).device
@@ -145,6 +150,19 @@ class NativeEngine:
         y = ops.conv(gr_relu, P[p + '.b2.c1'], want_relu=True)
         return ops.conv(y, P[p + '.b2.c2'], res=gr_raw, want_raw=True)
 
+    def _fuse_split(self, p, x_raw, x_relu, g_raw, g_relu, g_raw_lo=None):
+        """_fuse with the block outputs carried as (hi, lo): returns (raw, raw_lo)."""
+        P = self.P
+        sx = ops.conv(x_relu, P[p + '.b1.c1_x'], want_raw=True)
+        dx = ops.conv(x_raw, P[p + '.b1.ds_x'], want_raw=True)
+        y = ops.conv(g_relu, P[p + '.b1.c1_g'], res=sx, want_relu=True)
+        short = ops.conv_ex(g_raw, P[p + '.b1.ds_g'], res=dx, want_raw=True, want_lo=True)
+        g = ops.conv_ex(y, P[p + '.b1.c2'], res=short.raw, res_lo=short.raw_lo, want_raw=True, want_lo=True)
+        gr_raw, gr_lo, gr_relu = ops.cbam_residual_split(g.raw, g.raw_lo, self.cbam[p])
+        y = ops.conv(gr_relu, P[p + '.b2.c1'], want_relu=True)
+        out = ops.conv_ex(y, P[p + '.b2.c2'], res=gr_raw, res_lo=gr_lo, want_raw=True, want_lo=True)
+        return out.raw, out.raw_lo
+
     def _gru(self, key, g, h):
         # 3x3 conv over cat[g, h] -> (forget, update, new) gates -> h' (modules.py:145-149,163-167), one kernel:
         # the gates are evaluated on the fp32 accumulators in the conv epilogue, the 3C-channel tensor is never stored
@@ -207,18 +225,29 @@ class NativeEngine:
             h = h_all[i:i + step].contiguous()
             p16_raw, p16_relu = ops.conv(h, P[p + '.sensory_compress'], rank1_x=last[i:i + step].contiguous(),
                                          res=ro_all[i:i + step].contiguous(), want_raw=True, want_relu=True)
-            p16 = self._fuse(p + '.fuser', x_raw, x_relu, p16_raw, p16_relu)
-            g8_raw, g8_relu = ops.up2_add(p16, skip8)
-            q = p + '.up_16_8.out_conv'
-            y = ops.conv(g8_relu, P[q + '.c1'], want_relu=True)
-            short = ops.conv(g8_raw, P[q + '.ds'], want_raw=True)
-            p8 = ops.conv(y, P[q + '.c2'], res=short, want_raw=True)
-            g4_raw, g4_relu = ops.up2_add(p8, skip4)
+            g4_lo = None
+            if self.residual_lo:
+                p16, p16_lo = self._fuse_split(p + '.fuser', x_raw, x_relu, p16_raw, p16_relu)
+                g8_raw, g8_lo, g8_relu = ops.up2_add_split(p16, p16_lo, skip8)
+                q = p + '.up_16_8.out_conv'
+                y = ops.conv(g8_relu, P[q + '.c1'], want_relu=True)
+                short = ops.conv_ex(g8_raw, P[q + '.ds'], want_raw=True, want_lo=True)
+                o8 = ops.conv_ex(y, P[q + '.c2'], res=short.raw, res_lo=short.raw_lo, want_raw=True, want_lo=True)
+                p8 = o8.raw
+                g4_raw, g4_lo, g4_relu = ops.up2_add_split(p8, o8.raw_lo, skip4)
+            else:
+                p16 = self._fuse(p + '.fuser', x_raw, x_relu, p16_raw, p16_relu)
+                g8_raw, g8_relu = ops.up2_add(p16, skip8)
+                q = p + '.up_16_8.out_conv'
+                y = ops.conv(g8_relu, P[q + '.c1'], want_relu=True)
+                short = ops.conv(g8_raw, P[q + '.ds'], want_raw=True)
+                p8 = ops.conv(y, P[q + '.c2'], res=short, want_raw=True)
+                g4_raw, g4_relu = ops.up2_add(p8, skip4)
             q = p + '.up_8_4.out_conv'
             y = ops.conv(g4_relu, P[q + '.c1'], want_relu=True)
             # p4 = c2(...) + g4; the logit conv pred(relu(p4)) (big_modules.py:189-190) is folded in: the epilogue
             # emits the 9 per-tap dot products in fp32, a 3x3 gather finishes the convolution.
-            o4 = ops.conv_ex(y, P[q + '.c2'], res=g4_raw, want_raw=True, head_w=self.pred_w)
+            o4 = ops.conv_ex(y, P[q + '.c2'], res=g4_raw, res_lo=g4_lo, want_raw=True, head_w=self.pred_w)
             p4_raw = o4.raw
             logits = torch.empty(o4.head.shape[0], 4 * hh, 4 * ww, 1, dtype=torch.float32, device=o4.head.device)
             nat.head_gather3x3(o4.head, logits, self.pred_b, o4.head.shape[0], 4 * hh, 4 * ww)

@@ -197,6 +197,16 @@ def up2_add(g: torch.Tensor, skip: torch.Tensor, want_raw=True, want_relu=True):
     return raw, relu
 
 
+def up2_add_split(g: torch.Tensor, g_lo: torch.Tensor, skip: torch.Tensor):
+    """(g + g_lo) bilinear x2 + skip -> (raw, raw_lo, relu): the residual stream stays a fp16 hi/lo pair."""
+    b, h, w, c = g.shape
+    assert skip.shape == (1, 2 * h, 2 * w, c) and g_lo.shape == g.shape
+    raw = torch.empty(b, 2 * h, 2 * w, c, dtype=torch.float16, device=g.device)
+    raw_lo, relu = torch.empty_like(raw), torch.empty_like(raw)
+    nat.up2_add_split(g, g_lo, skip, raw, raw_lo, relu, b, h, w, c)
+    return raw, raw_lo, relu
+
+
 def area_down(x: torch.Tensor, r: int) -> torch.Tensor:
     b, h, w, c = x.shape
     y = torch.empty(b, h // r, w // r, c, dtype=torch.float16, device=x.device)
@@ -222,6 +232,17 @@ def cbam_residual(x: torch.Tensor, params: dict, want_raw=True, want_relu=True):
     nat.cbam(x, params['w1'], params['b1'], params['w2'], params['b2'], params['ws'], params['bs'], scratch, raw, relu,
              b, h, w, c, r)
     return raw, relu
+
+
+def cbam_residual_split(x: torch.Tensor, x_lo: torch.Tensor, params: dict):
+    """(x + x_lo) + CBAM(x) -> (raw, raw_lo, relu)."""
+    b, h, w, c = x.shape
+    r = params['w1'].shape[0]
+    scratch = torch.empty(33 * b * c + 2 * b * h * w, dtype=torch.float32, device=x.device)
+    raw, raw_lo, relu = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    nat.cbam_split(x, x_lo, params['w1'], params['b1'], params['w2'], params['b2'], params['ws'], params['bs'], scratch,
+                   raw, raw_lo, relu, b, h, w, c, r)
+    return raw, raw_lo, relu
 
 
 def gru(values: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
