@@ -43,3 +43,29 @@ def shifted_alignment(src_ti, src_image, src_mask, tar_ti, tar_image, *unused):
     d = tar_ti - src_ti
     moved = torch.roll(src_mask, shifts=(2 * d, -3 * d), dims=(1, 2))
     return torch.cat([torch.ones_like(moved[0:1]) * 0.5, moved], dim=0).unsqueeze(0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# match_and_merge scenario (segment_merging.py:17-143): tracked objects as (id, category, isthing, score) and three
+# detection rounds; rectangles are (y0, y1, x0, x1) on a 40 x 60 grid.
+MERGE_HW = (40, 60)
+MERGE_TRACKED = [(10, 1, True, 0.9), (11, 2, True, 0.8), (12, 7, False, 0.7), (13, None, None, None)]
+MERGE_OUR_BOXES = {1: (2, 18, 2, 20), 2: (20, 38, 4, 24), 3: (2, 30, 30, 58), 4: (32, 39, 40, 58)}  # by temporary id
+MERGE_ROUNDS = [
+    # (detections [(id, box, category, isthing, score)], incremental_mode, max_num_objects, our boxes override or None)
+    ([(21, (3, 19, 3, 21), 1, True, 0.6),      # IoU > 0.5 with object 10 -> merged
+      (22, (0, 8, 22, 28), 3, True, 0.5),      # new thing
+      (23, (4, 30, 32, 58), 7, False, 0.4),    # stuff, IoU > 0.5 with stuff 12 -> merged
+      (24, (30, 38, 14, 26), 2, True, 0.3),    # overlaps object 11 with IoU < 0.5 -> new object
+      (25, (32, 39, 42, 58), None, None, 0.2)  # untyped, IoU > 0.5 with untyped 13
+      ], False, -1, None),
+    ([(31, (20, 38, 4, 24), 2, True, 0.9)], True, -1, {1: (2, 18, 2, 20), 2: (20, 38, 4, 24), 3: (0, 0, 0, 0)}),
+    ([(41, (0, 5, 50, 60), 9, True, 0.9), (42, (2, 18, 2, 20), 1, True, 0.9)], False, 6, None),
+]
+
+
+def merge_masks(boxes, hw=MERGE_HW):
+    m = torch.zeros(*hw, dtype=torch.long)
+    for label, (y0, y1, x0, x1) in boxes.items():
+        m[y0:y1, x0:x1] = label
+    return m

@@ -242,6 +242,35 @@ def golden_consensus():
     json.dump(meta, open(os.path.join(HERE, 'consensus.json'), 'w'))
 
 
+def golden_match_and_merge():
+    """segment_merging.match_and_merge over three detection rounds (plain / incremental / object cap)."""
+    sys.path.insert(0, HERE)
+    import consensus_scenario as sc
+    import warnings
+    from deva.inference.object_info import ObjectInfo
+    from deva.inference.object_manager import ObjectManager
+    from deva.inference.segment_merging import match_and_merge
+    np.random.seed(5)
+    om = ObjectManager()
+    om.add_new_objects([ObjectInfo(i, category_id=c, isthing=t, score=s) for i, c, t, s in sc.MERGE_TRACKED])
+    our_boxes = dict(sc.MERGE_OUR_BOXES)
+    arrays, rounds = {}, []
+    for r, (dets, incremental, cap, override) in enumerate(sc.MERGE_ROUNDS):
+        if override is not None:
+            our_boxes = dict(override)
+        our = sc.merge_masks(our_boxes)
+        new = sc.merge_masks({d[0]: d[1] for d in dets})
+        infos = [ObjectInfo(d[0], category_id=d[2], isthing=d[3], score=d[4]) for d in dets]
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            one_hot = match_and_merge(our, new, om, infos, max_num_objects=cap, incremental_mode=incremental)
+        arrays[f'merge_{r}'] = one_hot.to(torch.uint8)
+        rounds.append([[t, o.id, o.poke_count, list(o.category_ids), list(o.scores)] for t, o in om.tmp_id_to_obj.items()])
+        print('  merge round', r, [(t, o.id, o.poke_count) for t, o in om.tmp_id_to_obj.items()])
+    save('match_and_merge.npz', **arrays)
+    json.dump({'rounds': rounds}, open(os.path.join(HERE, 'match_and_merge.json'), 'w'))
+
+
 if __name__ == '__main__':
     golden_spec()
     golden_memory_read()
@@ -249,3 +278,4 @@ if __name__ == '__main__':
     golden_network()
     golden_vos()
     golden_consensus()
+    golden_match_and_merge()

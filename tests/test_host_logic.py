@@ -128,6 +128,37 @@ def test_match_and_merge_matches_reference_logic():
         assert om.find_object_by_id(11).poke_count == 1
 
 
+def test_match_and_merge_matches_reference_fixture(golden_dir):
+    """Three detection rounds (plain, incremental, object cap) against outputs of the reference's match_and_merge
+    (tests/golden/make_golden.py::golden_match_and_merge): one-hot masks, ids, poke counts and merged meta bit-exact."""
+    import importlib.util
+    import json
+    import warnings
+    from deva.inference.object_info import ObjectInfo
+    from deva.inference.object_manager import ObjectManager
+    from deva.inference.segment_merging import match_and_merge
+    spec = importlib.util.spec_from_file_location('consensus_scenario', os.path.join(golden_dir, 'consensus_scenario.py'))
+    sc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sc)
+    g = np.load(os.path.join(golden_dir, 'match_and_merge.npz'))
+    want = json.load(open(os.path.join(golden_dir, 'match_and_merge.json')))['rounds']
+    np.random.seed(5)
+    om = ObjectManager()
+    om.add_new_objects([ObjectInfo(i, category_id=c, isthing=t, score=s) for i, c, t, s in sc.MERGE_TRACKED])
+    our_boxes = dict(sc.MERGE_OUR_BOXES)
+    for r, (dets, incremental, cap, override) in enumerate(sc.MERGE_ROUNDS):
+        if override is not None:
+            our_boxes = dict(override)
+        infos = [ObjectInfo(d[0], category_id=d[2], isthing=d[3], score=d[4]) for d in dets]
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            one_hot = match_and_merge(sc.merge_masks(our_boxes), sc.merge_masks({d[0]: d[1] for d in dets}), om, infos,
+                                      max_num_objects=cap, incremental_mode=incremental)
+        assert torch.equal(one_hot.to(torch.uint8), torch.from_numpy(g[f'merge_{r}'])), r
+        state = [[t, o.id, o.poke_count, o.category_ids, o.scores] for t, o in om.tmp_id_to_obj.items()]
+        assert state == want[r], (r, state, want[r])
+
+
 def test_pad_unpad_roundtrip_property():
     """pad_divide_by / unpad (tensor_utils.py:7-48) for arbitrary sizes: multiple of d, symmetric with the odd pixel at
     the bottom/right, zero filled, exact round trip - and identical to the oracle."""
