@@ -69,3 +69,44 @@ def merge_masks(boxes, hw=MERGE_HW):
     for label, (y0, y1, x0, x1) in boxes.items():
         m[y0:y1, x0:x1] = label
     return m
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ObjectManager script (object_manager.py:8-168): the same operations are replayed on the reference (when the fixture is
+# minted) and on the product; `snapshot` is what gets compared after every operation.
+def object_manager_script(ObjectManager, ObjectInfo, np_seed: int = 11):
+    import numpy as np
+    np.random.seed(np_seed)
+    om = ObjectManager()
+    log = []
+
+    def snapshot(tag, extra=None):
+        log.append({'op': tag, 'extra': extra,
+                    'tmp_to_obj': [[int(t), int(o.id)] for t, o in om.tmp_id_to_obj.items()],
+                    'obj_to_tmp': [[int(o.id), int(t)] for o, t in om.obj_to_tmp_id.items()],
+                    'history': sorted(int(i) for i in om.all_historical_object_ids),
+                    'all_obj_ids': [int(i) for i in om.all_obj_ids], 'num_obj': int(om.num_obj),
+                    'segments': om.get_current_segments_info()})
+
+    snapshot('init')
+    snapshot('add ints', [list(map(int, r)) for r in om.add_new_objects([1, 2, 5])])
+    snapshot('add colliding int', [list(map(int, r)) for r in om.add_new_objects([2])])  # random re-id in 1..255
+    snapshot('add infos', [list(map(int, r)) for r in om.add_new_objects(
+        [ObjectInfo(9, category_id=3, isthing=True, score=0.5), ObjectInfo(1, category_id=4, isthing=False, score=0.25)])])
+    om.find_object_by_id(5).merge(ObjectInfo(77, category_id=8, isthing=True, score=0.75))
+    om.find_object_by_id(5).merge(ObjectInfo(78, category_id=8, isthing=True, score=0.5))
+    snapshot('merge meta into 5')
+    mask = torch.arange(7).repeat(3, 1)
+    snapshot('tmp_to_obj_cls', om.tmp_to_obj_cls(mask).tolist())
+    snapshot('make_one_hot', om.make_one_hot(om.tmp_to_obj_cls(mask)).to(torch.uint8).tolist())
+    om.delete_object(2)
+    snapshot('delete 2')
+    for oid, pokes in ((1, 3), (9, 6)):
+        for _ in range(pokes):
+            om.find_object_by_id(oid).poke()
+    snapshot('purge > 4', [list(map(int, r)) if isinstance(r, list) else bool(r) for r in om.purge_inactive_objects(4)])
+    snapshot('purge > 0', [list(map(int, r)) if isinstance(r, list) else bool(r) for r in om.purge_inactive_objects(0)])
+    om.use_long_id = True
+    snapshot('add with long ids', [list(map(int, r)) for r in om.add_new_objects([5, 300])])  # 5 < 256 -> re-id >= 256
+    snapshot('has_all of an unknown id', bool(om.has_all([4242])))  # known ids crash in the reference
+    return log

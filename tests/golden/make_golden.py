@@ -271,6 +271,17 @@ def golden_match_and_merge():
     json.dump({'rounds': rounds}, open(os.path.join(HERE, 'match_and_merge.json'), 'w'))
 
 
+def golden_object_manager():
+    """ObjectManager / ObjectInfo bookkeeping script (ids, random re-ids, deletion, purging, votes): integer-exact."""
+    sys.path.insert(0, HERE)
+    import consensus_scenario as sc
+    from deva.inference.object_info import ObjectInfo
+    from deva.inference.object_manager import ObjectManager
+    log = sc.object_manager_script(ObjectManager, ObjectInfo)
+    json.dump(log, open(os.path.join(HERE, 'object_manager.json'), 'w'))
+    print('wrote object_manager.json', len(log), 'snapshots; final', log[-2]['tmp_to_obj'])
+
+
 if __name__ == '__main__':
     golden_spec()
     golden_memory_read()
@@ -279,3 +290,4 @@ if __name__ == '__main__':
     golden_vos()
     golden_consensus()
     golden_match_and_merge()
+    golden_object_manager()

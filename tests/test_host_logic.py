@@ -159,6 +159,23 @@ def test_match_and_merge_matches_reference_fixture(golden_dir):
         assert state == want[r], (r, state, want[r])
 
 
+def test_object_manager_script_matches_reference_fixture(golden_dir):
+    """Ids, random re-ids (numpy global RNG), deletion with re-packing, purging, votes, id-map conversions: every
+    snapshot of the scripted session equals the one recorded from the reference's ObjectManager."""
+    import importlib.util
+    import json
+    from deva.inference.object_info import ObjectInfo
+    from deva.inference.object_manager import ObjectManager
+    spec = importlib.util.spec_from_file_location('consensus_scenario', os.path.join(golden_dir, 'consensus_scenario.py'))
+    sc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sc)
+    want = json.load(open(os.path.join(golden_dir, 'object_manager.json')))
+    got = json.loads(json.dumps(sc.object_manager_script(ObjectManager, ObjectInfo)))
+    assert len(got) == len(want)
+    for a_, b_ in zip(got, want):
+        assert a_ == b_, (a_['op'], a_, b_)
+
+
 def test_pad_unpad_roundtrip_property():
     """pad_divide_by / unpad (tensor_utils.py:7-48) for arbitrary sizes: multiple of d, symmetric with the odd pixel at
     the bottom/right, zero filled, exact round trip - and identical to the oracle."""
