@@ -282,6 +282,16 @@ def golden_object_manager():
     print('wrote object_manager.json', len(log), 'snapshots; final', log[-2]['tmp_to_obj'])
 
 
+def golden_eval_args():
+    from argparse import ArgumentParser
+    from deva.inference.eval_args import add_common_eval_args
+    p = ArgumentParser()
+    add_common_eval_args(p)
+    ref = {a.dest: [a.default, type(a).__name__, (a.type.__name__ if a.type else None)] for a in p._actions if a.dest != 'help'}
+    json.dump(ref, open(os.path.join(HERE, 'eval_args.json'), 'w'), indent=0)
+    print('wrote eval_args.json', len(ref))
+
+
 if __name__ == '__main__':
     golden_spec()
     golden_memory_read()
@@ -291,3 +301,4 @@ if __name__ == '__main__':
     golden_consensus()
     golden_match_and_merge()
     golden_object_manager()
+    golden_eval_args()

@@ -176,6 +176,18 @@ def test_object_manager_script_matches_reference_fixture(golden_dir):
         assert a_ == b_, (a_['op'], a_, b_)
 
 
+def test_eval_args_match_reference_fixture(golden_dir):
+    """add_common_eval_args (eval_args.py:7-44): same flags, defaults, types and store_true actions as the reference
+    (fixture = the reference parser's actions, dumped when the fixtures were minted)."""
+    import json
+    from argparse import ArgumentParser
+    from deva.inference.eval_args import add_common_eval_args
+    p = ArgumentParser()
+    add_common_eval_args(p)
+    mine = {a.dest: [a.default, type(a).__name__, (a.type.__name__ if a.type else None)] for a in p._actions if a.dest != 'help'}
+    assert mine == json.load(open(os.path.join(golden_dir, 'eval_args.json')))
+
+
 def test_pad_unpad_roundtrip_property():
     """pad_divide_by / unpad (tensor_utils.py:7-48) for arbitrary sizes: multiple of d, symmetric with the odd pixel at
     the bottom/right, zero filled, exact round trip - and identical to the oracle."""
