@@ -110,3 +110,26 @@ def object_manager_script(ObjectManager, ObjectInfo, np_seed: int = 11):
     snapshot('add with long ids', [list(map(int, r)) for r in om.add_new_objects([5, 300])])  # 5 < 256 -> re-id >= 256
     snapshot('has_all of an unknown id', bool(om.has_all([4242])))  # known ids crash in the reference
     return log
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Semi-online session (inference_core.py:137-290): detections merged at t = 0, 3, 5, 6, plain propagation in between.
+DETECT_HW = (90, 120)
+DETECT_CONFIG_EXTRA = dict(max_missed_detection_count=1, max_num_objects=-1, mem_every=2)
+# t -> None (step) or list of (id, box, category, isthing, score)
+DETECT_SESSION = [
+    [(3, (10, 50, 20, 70), 1, True, 0.9), (5, (55, 85, 60, 110), 2, True, 0.8)],
+    None,
+    None,
+    [(1, (10, 50, 20, 70), 1, True, 0.7), (4, (4, 30, 84, 118), 3, True, 0.6)],
+    None,
+    [],
+    [(8, (60, 88, 4, 40), 5, False, 0.5)],
+    None,
+]
+
+
+def detect_frames(seed: int = 33):
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn(3, *DETECT_HW, generator=g)
+    return [base + 0.2 * torch.randn(3, *DETECT_HW, generator=g) for _ in DETECT_SESSION]

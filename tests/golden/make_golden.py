@@ -292,6 +292,37 @@ def golden_eval_args():
     print('wrote eval_args.json', len(ref))
 
 
+def golden_detections():
+    """incorporate_detection + step over a semi-online session (inference_core.py:137-290): probabilities, object
+    manager state (ids, poke counts, merged meta) and bank sizes after every call."""
+    sys.path.insert(0, HERE)
+    import consensus_scenario as sc
+    from deva.inference.object_info import ObjectInfo
+    sd = param_spec.synthetic_state_dict(seed=1)
+    cfg = dict(CFG, **sc.DETECT_CONFIG_EXTRA)
+    net = DEVA(cfg).eval()
+    net.load_weights(sd)
+    np.random.seed(42)
+    core = DEVAInferenceCore(net, cfg)
+    frames = sc.detect_frames()
+    arrays, states = {}, []
+    for t, (frame, dets) in enumerate(zip(frames, sc.DETECT_SESSION)):
+        if dets is None:
+            p = core.step(frame, end=(t == len(frames) - 1))
+        else:
+            ids = sc.merge_masks({d[0]: d[1] for d in dets}, sc.DETECT_HW)
+            infos = [ObjectInfo(d[0], category_id=d[2], isthing=d[3], score=d[4]) for d in dets]
+            p = core.incorporate_detection(frame, ids, infos)
+        arrays[f'prob_{t:02d}'] = p.clone()
+        mem = core.memory
+        states.append({'objects': [[tt, o.id, o.poke_count, list(o.category_ids), list(o.scores)]
+                                   for tt, o in core.object_manager.tmp_id_to_obj.items()],
+                       'sizes': {str(b): [mem.work_mem.size(b), mem.long_mem.size(b)] for b in mem.work_mem.buckets}})
+        print('  detections t', t, 'prob', tuple(p.shape), states[-1]['objects'], states[-1]['sizes'])
+    save('detections.npz', **arrays)
+    json.dump({'config': cfg, 'states': states}, open(os.path.join(HERE, 'detections.json'), 'w'))
+
+
 if __name__ == '__main__':
     golden_spec()
     golden_memory_read()
@@ -302,3 +333,4 @@ if __name__ == '__main__':
     golden_match_and_merge()
     golden_object_manager()
     golden_eval_args()
+    golden_detections()

@@ -155,3 +155,27 @@ def test_consensus_voting_matches_reference(golden_dir, synthetic_sd):
     want = meta['auto']['real_first']
     assert kti == want['keyframe'] and [list(i) for i in infos] == want['segments']
     assert torch.equal(mask, g['auto_real_first_mask'])
+
+
+def test_detection_session_matches_reference(golden_dir, synthetic_sd):
+    """incorporate_detection (match & merge, poke / purge, new buckets, memory purge) interleaved with step():
+    probabilities to fp32 round-off, ids / poke counts / merged meta / bank sizes exact."""
+    from oracle.detections import DetectionCoreOracle, Tracked
+    sc = _scenario(golden_dir)
+    g = _load(golden_dir, 'detections.npz')
+    meta = json.load(open(os.path.join(golden_dir, 'detections.json')))
+    np.random.seed(42)
+    core = DetectionCoreOracle(synthetic_sd, meta['config'])
+    frames = sc.detect_frames()
+    for t, (frame, dets) in enumerate(zip(frames, sc.DETECT_SESSION)):
+        if dets is None:
+            p = core.step(frame, end=(t == len(frames) - 1))
+        else:
+            ids = sc.merge_masks({d[0]: d[1] for d in dets}, sc.DETECT_HW)
+            p = core.incorporate_detection(frame, ids, [Tracked(d[0], d[2], d[3], d[4]) for d in dets])
+        want = meta['states'][t]
+        objects = [[tt, o.id, o.poke_count, list(o.category_ids), list(o.scores)] for tt, o in core.objects.by_tmp.items()]
+        assert objects == want['objects'], (t, objects, want['objects'])
+        sizes = {str(b): list(s) for b, s in core.memory.sizes().items()}
+        assert sizes == want['sizes'], (t, sizes, want['sizes'])
+        torch.testing.assert_close(p, g[f'prob_{t:02d}'], rtol=1e-4, atol=2e-5)
