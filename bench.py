@@ -13,11 +13,15 @@ each rank propagates its own clip (clip-parallel, weak scaling, NCCL barrier onl
 Printed JSON line: metric/value/unit/... plus
   roofline      fused affinity path (pack_query + similarity/top-k/softmax + readout GEMM), algorithmic
                 FLOPs 2*N*Q*2CK + 2*K*CV*N*Q per frame / CUDA-event time per frame, vs measured bf16 peak;
+                roofline_conv: the same for the convolution stack (algorithmic conv FLOPs / CUDA-event time);
   e2e           same FPS through the public API with host frames (pinned H2D of every frame, D2H of the id mask);
-  cpu_baseline  the CPU oracle (port of the reference, oracle/) on this box's host cores, bounded sample;
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, staged by oracle/build_ref.py) on this box's host cores, on a
+                bounded sample (all shared stages + `--ref-objects` of the K objects, linearly extrapolated and flagged);
+  torch_gpu_baseline  the unmodified reference on the SAME B200 (all K objects): fp32 (PyTorch's TF32 default), fp32
+                with TF32 off, and --amp (fp16 autocast, evaluation/eval_vos.py:137) - the real bar;
   clocks        SM clock / throttle reasons sampled with nvidia-smi during the timed region.
-``--impl reference`` times the CPU oracle instead (the reference is pure Python/PyTorch; its CPU path is what
-``oracle/`` restates and pins to reference-minted fixtures).
+``--impl reference`` times the reference's own ``DEVAInferenceCore.step`` on the host cores (``oracle/_ref``; the
+oracle port only when the staged copy is missing).
 """
 import argparse
 import json
@@ -245,6 +249,20 @@ def run_ours(args):
         clip.step_e2e_fused_io()
     ms_e2e_io, _ = timed(clip.step_e2e_fused_io, args.steps, dist_on)
 
+    # conv-stack roofline: a separate short pass with CUDA events around every conv launch (not part of `value`)
+    from deva.model import native_ops
+    precision = getattr(clip.core.network.engine, 'precision', 'n/a')
+    conv_roof = None
+    if rank == 0:
+        native_ops.PROFILE = []
+        for _ in range(5):  # exactly one memory frame
+            clip.step_resident()
+        torch.cuda.synchronize()
+        prof, native_ops.PROFILE = native_ops.PROFILE, None
+        conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof) / 5
+        conv_flops = sum(f for _, _, f, _ in prof) / 5
+        mma_flops = sum(f * n for _, _, f, n in prof) / 5
+
     if rank == 0:
         peaks = {}
         try:
@@ -256,41 +274,55 @@ def run_ours(args):
             'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
         flops = read_flops(wl, clip.q)
         achieved = flops / (read_ms * 1e-3) / 1e12
-        traffic = None
+        traffic = conv_traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get(args.workload)  # readout_sparse_kernel
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')))
+            traffic = tr.get(args.workload)  # readout_sparse_kernel, per launch
+            conv_traffic = tr.get(args.workload + '_conv')
         except Exception:
             pass
+        conv_ach = conv_flops / (conv_ms * 1e-3) / 1e12
+        conv_roof = {'kernel': 'conv_kernel (tcgen05 implicit GEMM), all launches of a frame', 'bound': 'tensor',
+                     'achieved': conv_ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': conv_ach / peak,
+                     'traffic': conv_traffic, 'ms_per_frame': conv_ms, 'flops_per_frame': conv_flops,
+                     'what': 'algorithmic FLOPs 2*B*Ho*Wo*Cout*k*k*Cin per layer (extra split-precision passes NOT counted) / '
+                             'CUDA-event time of the conv launches, 5-frame pass incl. one memory frame',
+                     'executed_tflops': mma_flops / (conv_ms * 1e-3) / 1e12}
         h2d = int(clip.frames_host[0].numel() * 4)
         d2h = int(wl['h'] * wl['w'])
         out = {
             'metric': METRIC, 'value': world * args.steps / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16 operands / f32 accumulate '
-            '(tcgen05 memory read + conv stack); key path split-f16x3 (~f32)', 'data': 'synthetic',
-            'config': {'workload': wl['name'], 'frame': [wl['h'], wl['w']], 'query_positions': clip.q,
-                       'objects': wl['k'], 'memory_slots': wl['n'], 'mem_every': 5, 'top_k': TOP_K,
-                       'parallelism': f'clip-parallel x{world}' if world > 1 else 'single clip',
-                       'l2': 'per-step working set (activations > 2 GB) exceeds the 126 MB L2; no explicit flush',
-                       'weights': 'synthetic_state_dict(seed=0), real architecture (69.2 M parameters)'},
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16 MMA operands / f32 accumulate '
+            f'(tcgen05 memory read + conv stack), precision plan {precision!r}; key path split-f16x3 (~f32)', 'data': 'synthetic',
+            'config': workload_config(wl, clip.q, world),
             'roofline': {'kernel': 'fused affinity path: pack_query + sim_topk(tcgen05 fp16x3) + merge + bucket + readout_sparse(tcgen05, '
-                                   'affinity tiles built in smem); traffic = DRAM bytes of readout_sparse_kernel (ncu)',
+                                   'affinity tiles built in smem); traffic = DRAM bytes of readout_sparse_kernel (ncu, the fp16 '
+                                   'token-major output variant the step runs)',
                          'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'ms_per_launch': read_ms, 'flops_per_launch': flops},
+            'roofline_conv': conv_roof,
             'e2e': {'value': world * args.steps / (ms_e2e * 1e-3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h},
             'e2e_fused_io': {'value': world * args.steps / (ms_e2e_io * 1e-3), 'unit': 'frames/s',
                              'h2d_bytes_per_step': int(wl['h'] * wl['w'] * 3), 'd2h_bytes_per_step': d2h,
                              'what': 'uint8 frame upload + on-device normalise; fused argmax + id remap (deva.inference.frame_io)'},
             'gpu_launches': int(launches), 'wall_ms_per_step': wall / args.steps, 'clocks': clocks,
-            'cpu_baseline': cpu_baseline(wl, budget_s=25.0),
+            'precision_plan': precision,
         }
+        del clip  # give the baseline legs the device
+        torch.cuda.empty_cache()
+        if world == 1 and not args.no_cpu_baseline:
+            try:  # bounded sample: 1 warm-up + 2 timed sample steps of the unmodified reference on the host cores
+                leg = _run_leg(['--impl', 'reference', '--steps', '2', '--warmup', '1', '--workload', args.workload,
+                                '--ref-objects', str(args.ref_objects)], timeout=900)
+                out['cpu_baseline'] = leg['cpu_baseline']
+            except Exception as exc:
+                out['cpu_baseline'] = {'error': f'{type(exc).__name__}: {exc}'[:300]}
         if world == 1 and not args.no_torch_baseline:
-            del clip  # give the stock-PyTorch pass the whole device
-            torch.cuda.empty_cache()
             try:
-                out['torch_gpu_baseline'] = torch_gpu_baseline(wl, device)
+                out['torch_gpu_baseline'] = _run_leg(['--impl', 'reference_gpu', '--workload', args.workload], timeout=900)
             except Exception as exc:  # reported extra, never fatal for the bench line
                 out['torch_gpu_baseline'] = {'error': f'{type(exc).__name__}: {exc}'[:300]}
         print(json.dumps(out))
@@ -299,7 +331,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# ------------------------------------------------------------------------------------------- CPU oracle
+# ------------------------------------------------------ fallback: the oracle port, stage by stage
 def _oracle_stages(wl, budget_s, device, k_s):
     """One frame of the reference algorithm (the oracle's fp32 PyTorch restatement) on ``device``, stage by stage.
     Returns wall-clock seconds per stage; per-object stages run on ``k_s`` objects."""
@@ -359,7 +391,7 @@ def _blend(st, scale):
     return per_frame
 
 
-def cpu_baseline(wl, budget_s):
+def cpu_baseline_port(wl, budget_s):
     """Reference-algorithm frame rate on the host cores: the oracle's stages on a bounded sample.
 
     Object-independent stages run in full; per-object stages run on ``k_s`` of the K objects and are scaled by
@@ -377,22 +409,181 @@ def cpu_baseline(wl, budget_s):
                         'decode_per_obj': st['decode'], 'encode_mask_per_obj': st['encode_mask']}}
 
 
-def torch_gpu_baseline(wl, device):
-    """SURVEY 8(d) "GPU-side comparison": the same reference algorithm as stock PyTorch ops (cuDNN / cuBLAS fp32,
-    PyTorch's default TF32 policy) on the same B200, all K objects in one batch; per-stage best of three warm passes.  A reported baseline only - none of it is on the product path."""
+# ---------------------------------------------------------------------- unmodified reference (oracle/_ref)
+def workload_config(wl, q, world):
+    """The `config` object of the JSON line - identical for the product arm and the reference arm."""
+    return {'workload': wl['name'], 'frame': [wl['h'], wl['w']], 'query_positions': q, 'objects': wl['k'],
+            'memory_slots': wl['n'], 'mem_every': 5, 'top_k': TOP_K,
+            'parallelism': f'clip-parallel x{world}' if world > 1 else 'single clip',
+            'l2': 'per-step working set (activations > 2 GB) exceeds the 126 MB L2; no explicit flush',
+            'weights': 'synthetic_state_dict(seed=0), real architecture (69.2 M parameters)'}
+
+
+class RefClip:
+    """The same clip as ``Clip`` driven through the UNMODIFIED reference (DEVA + DEVAInferenceCore from oracle/_ref):
+    same seeded frames, masks, checkpoint and random bank top-up; ``n_obj`` of the workload's objects."""
+    def __init__(self, wl, device, n_obj, seed):
+        from oracle import ref_loader
+        DEVA, Core, synth = ref_loader.load()
+        self.wl, self.device, self.n_obj = wl, device, n_obj
+        cfg = base_config()
+        net = DEVA(cfg).to(device).eval()
+        net.load_weights({k: v.to(device) for k, v in synth(seed=0).items()})
+        self.net = net
+        self.core = Core(net, cfg)
+        self.frames = synth_frames(wl, 5, seed).to(device)
+        ids = list(range(1, n_obj + 1))
+        mask = synth_mask(wl)
+        mask[mask > n_obj] = 0
+        self.core.step(self.frames[0], mask.to(device), ids)
+        mem = self.core.memory
+        self.bucket = next(iter(mem.work_mem.buckets))
+        self.q = mem.HW
+        extra = wl['n'] - mem.work_mem.size(self.bucket)
+        assert extra >= 0
+        if extra > 0:
+            g = torch.Generator().manual_seed(seed + 1)
+            key = torch.randn(1, CK, extra, 1, generator=g).to(device)
+            shr = (1 + torch.rand(1, 1, extra, 1, generator=g)).to(device)
+            sel = torch.sigmoid(torch.randn(1, CK, extra, 1, generator=g)).to(device)
+            val = torch.randn(1, n_obj, CV, extra, 1, generator=g).to(device)
+            mem.add_memory(key, shr, val, ids, selection=sel)
+        assert mem.work_mem.size(self.bucket) == wl['n']
+        self.i = 0
+
+    def clamp(self):
+        """Keep the configuration the named one: drop what a memory frame just appended (kv_memory_store.py:35-116)."""
+        if self.core.last_mem_ti != self.core.curr_ti:
+            return
+        wm, b, n = self.core.memory.work_mem, self.bucket, self.wl['n']
+        wm.k[b], wm.s[b], wm.e[b] = wm.k[b][:, :n], wm.s[b][:, :n], wm.e[b][:, :n]
+        wm.use_cnt[b], wm.life_cnt[b] = wm.use_cnt[b][:n], wm.life_cnt[b][:n]
+        for obj in wm.buckets[b]:
+            wm.v[obj] = wm.v[obj][:, :n]
+
+    def step(self):
+        p = self.core.step(self.frames[self.i % 5])
+        self.clamp()
+        self.i += 1
+        return p
+
+
+class _SharedTimer:
+    """Accumulates the wall time of the object-independent stages of a reference step (CPU: calls are synchronous):
+    encode_image, transform_key (network.py:42-68) and get_similarity / do_softmax (memory_utils.py:6-76)."""
+    def __init__(self, net):
+        import deva.inference.memory_manager as mmod  # the reference's (oracle/_ref)
+        self.total = 0.0
+        self._undo = []
+        for obj, name in ((net, 'encode_image'), (net, 'transform_key'), (mmod, 'get_similarity'), (mmod, 'do_softmax')):
+            fn = getattr(obj, name)
+            setattr(obj, name, self._wrap(fn))
+            self._undo.append((obj, name, fn))
+
+    def _wrap(self, fn):
+        def timed_fn(*a, **k):
+            t0 = time.perf_counter()
+            try:
+                return fn(*a, **k)
+            finally:
+                self.total += time.perf_counter() - t0
+        return timed_fn
+
+    def close(self):
+        for obj, name, fn in self._undo:
+            setattr(obj, name, fn)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_cpu(wl, steps, warmup, n_obj):
+    """The reference's own step() on the host cores.  A step of the sample is one full-resolution frame of the named
+    workload with ``n_obj`` of its K objects; every per-object stage of DEVA is independent across objects (the
+    reference's own note, docs/DEMO.md:41: run time is linear in the number of objects), so the full-frame time is
+    shared + K * per_object with both terms MEASURED here.  Returns the cpu_baseline record."""
+    cores = host_cores()
+    torch.set_num_threads(cores)
+    torch.set_grad_enabled(False)
     k = wl['k']
-    st = None
-    for i in range(4):  # pass 0 pays cuDNN's algorithm search; keep the per-stage best of the others
-        cur = _oracle_stages(wl, 1e9, device, k)
+    n_obj = max(1, min(n_obj, k))
+    t_build = time.perf_counter()
+    clip = RefClip(wl, 'cpu', n_obj, seed=100)
+    t_build = time.perf_counter() - t_build
+    for _ in range(warmup):
+        clip.step()
+    timer = _SharedTimer(clip.net)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        clip.step()
+    wall = time.perf_counter() - t0
+    timer.close()
+    t_step = wall / steps
+    t_shared = timer.total / steps
+    t_obj = max(t_step - t_shared, 0.0) / n_obj
+    frame_s = t_shared + k * t_obj
+    return {'value': 1.0 / frame_s, 'unit': 'frames/s', 'cores': cores, 'kind': 'reference',
+            'extrapolated': n_obj < k,
+            'sample': f'{steps} timed (+{warmup} warm-up) steps of the unmodified reference DEVAInferenceCore.step (oracle/_ref, '
+                      f'fp32, torch {torch.__version__}, {cores} threads) on full {wl["h"]}x{wl["w"]} frames, N={wl["n"]} slots, '
+                      f'{n_obj} of {k} objects per step, every 5th step a memory frame; full-frame time = shared + {k} x per-object, '
+                      f'both measured',
+            'measured': {'objects_in_sample': n_obj, 's_per_sample_step': t_step, 's_shared_per_step': t_shared,
+                         's_per_object': t_obj, 's_full_frame': frame_s, 'timed_wall_s': wall, 'setup_s': t_build},
+            'q': clip.q}
+
+
+def reference_gpu(wl, device, steps=5, warmup=2):
+    """SURVEY 8(d) "GPU-side comparison": the UNMODIFIED reference on the same B200, all K objects, through its public
+    step(): fp32 under PyTorch's default TF32 policy (what a user of the reference gets), fp32 with TF32 forbidden
+    (the precision the 1e-3 parity contract is written against) and --amp (evaluation/eval_vos.py:137)."""
+    torch.set_grad_enabled(False)
+    out = {'kind': 'unmodified reference (oracle/_ref) on cuda', 'objects': wl['k'], 'steps': steps, 'warmup': warmup,
+           'sample': f'{steps} frames {wl["h"]}x{wl["w"]} incl. one memory frame, N={wl["n"]}, all {wl["k"]} objects'}
+    torch.backends.cudnn.benchmark = True
+    for mode in ('fp32_tf32_default', 'fp32_strict', 'amp_fp16'):
+        torch.backends.cudnn.allow_tf32 = mode != 'fp32_strict'
+        torch.backends.cuda.matmul.allow_tf32 = mode != 'fp32_strict'  # eval scripts leave matmul at PyTorch's default (off)
+        if mode == 'fp32_tf32_default':
+            torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            with torch.autocast('cuda', dtype=torch.float16, enabled=(mode == 'amp_fp16')):
+                clip = RefClip(wl, device, wl['k'], seed=100)
+                for _ in range(warmup):
+                    clip.step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    clip.step()
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {'value': 1e3 / ms, 'unit': 'frames/s', 'ms_per_step': ms,
+                         'max_allocated_gb': torch.cuda.max_memory_allocated() / 2**30}
+            del clip
+        except Exception as exc:  # a reported extra, never fatal
+            out[mode] = {'error': f'{type(exc).__name__}: {exc}'[:300]}
         torch.cuda.empty_cache()
-        if i == 1:
-            st = cur
-        elif i > 1:
-            st = {name: min(st[name], cur[name]) for name in st}
-    return {'value': 1.0 / _blend(st, 1.0), 'unit': 'frames/s', 'kind': 'oracle ops on cuda (stock PyTorch fp32)',
-            'tf32': {'cudnn': bool(torch.backends.cudnn.allow_tf32), 'matmul': bool(torch.backends.cuda.matmul.allow_tf32)},
-            'sample': f'1 frame {wl["h"]}x{wl["w"]}, N={wl["n"]}, all {k} objects; value encoder weighted 1 frame in 5',
-            'stage_s': st}
+        torch.cuda.reset_peak_memory_stats()
+    return out
+
+
+def _run_leg(args_list, timeout):
+    """Run another leg of this script in its own process (the reference's package is also called `deva`)."""
+    cmd = [sys.executable, os.path.abspath(__file__)] + args_list
+    env = dict(os.environ)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT'):
+        env.pop(k, None)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith('{'):
+            return json.loads(line)
+    raise RuntimeError(f'leg {args_list} printed no JSON (rc {r.returncode}): {r.stderr[-300:]}')
 
 
 def run_reference(args):
@@ -400,18 +591,28 @@ def run_reference(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    vals = []
-    for _ in range(max(1, min(args.steps, 2))):
-        vals.append(cpu_baseline(wl, budget_s=40.0))
-    best = max(vals, key=lambda v: v['value'])
-    out = {'impl': 'reference', 'metric': METRIC, 'value': best['value'], 'unit': 'frames/s', 'n_gpus': world,
-           'steps': len(vals), 'warmup': 0, 'ms_per_step': 1e3 / best['value'], 'higher_is_better': True,
+    from oracle import ref_loader
+    if ref_loader.available():
+        base = reference_cpu(wl, args.steps, max(args.warmup, 1), args.ref_objects)
+        q = base.pop('q')
+        ms_step = base['measured']['s_per_sample_step'] * 1e3
+    else:  # staged copy missing: the oracle port, stage by stage (kind 'port')
+        base = cpu_baseline_port(wl, budget_s=40.0)
+        q = (-(-wl['h'] // 16)) * (-(-wl['w'] // 16))
+        ms_step = 1e3 / base['value']
+    out = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'frames/s', 'n_gpus': world,
+           'steps': args.steps, 'warmup': max(args.warmup, 1), 'ms_per_step': ms_step, 'higher_is_better': True,
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': wl['name'], 'frame': [wl['h'], wl['w']], 'objects': wl['k'],
-                      'memory_slots': wl['n']},
-           'cpu_baseline': best,
-           'e2e': {'value': best['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+           'extrapolated': bool(base.get('extrapolated', True)),
+           'ms_per_step_is': 'measured time of one SAMPLE step (see cpu_baseline.sample); value = 1 / (shared + K x per-object)',
+           'config': workload_config(wl, q, world), 'cpu_baseline': base, 'gpu_launches': 0,
+           'e2e': {'value': base['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(out))
+
+
+def run_reference_gpu(args):
+    torch.cuda.set_device(0)
+    print(json.dumps(reference_gpu(WORKLOADS[args.workload], torch.device('cuda', 0))))
 
 
 if __name__ == '__main__':
@@ -419,11 +620,16 @@ if __name__ == '__main__':
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference_gpu'])
+    ap.add_argument('--ref-objects', type=int, default=1,
+                    help='objects per sample step of the CPU reference leg (the rest is extrapolated linearly and flagged)')
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the host-cores reference leg')
     ap.add_argument('--workload', default='c3', choices=list(WORKLOADS))
     ap.add_argument('--no-torch-baseline', action='store_true', help='skip the stock-PyTorch-on-GPU comparison pass')
     a = ap.parse_args()
     if a.impl == 'reference':
         run_reference(a)
+    elif a.impl == 'reference_gpu':
+        run_reference_gpu(a)
     else:
         run_ours(a)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DEVA_B200_ABI_VERSION 9
+#define DEVA_B200_ABI_VERSION 10
 #define DEVA_B200_LIST_PITCH 32 /* row pitch of top-k outputs == max supported top_k */
 #define DEVA_B200_MAX_GROUPS 256 /* objects per deva_b200_readout call */
 
@@ -166,6 +166,9 @@ typedef struct deva_b200_conv_desc {
   const void* x_lo;     /* optional fp16 low-order part of x (x_true = x + x_lo): split-precision mode
                          * D = Xh.Wh + Xl.Wh + Xh.Wl with weights packed [cout_pad, 2 (hi, lo), kh*kw, cin_pad];
                          * ~fp32 accuracy at 3x the MMA work.  Exclusive with x2. */
+  int32_t split_mode;   /* 0: as described above (x_lo => three passes);  1: x_lo with SINGLE fp16 weights,
+                         * D = Xh.W + Xl.W (removes the activation-operand rounding, 2x the MMA work);  2: no x_lo,
+                         * weights packed (hi, lo) as for mode 0, D = X.Wh + X.Wl (removes the weight rounding) */
   int32_t batch, h, w, cin_pad;
   const void* w_packed; /* fp16 [cout_pad, kh*kw*cin_pad] */
   int32_t kh, kw, stride; /* 1x1 or 3x3, stride 1 or 2, padding kh/2 (nn.Conv2d semantics) */
@@ -216,13 +219,17 @@ DEVA_B200_API int deva_b200_area_down_plane(const float* x, float* y, int b, int
 DEVA_B200_API int deva_b200_cbam(const void* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                  const float* ws, const float* bs, float* scratch, void* raw, void* relu, int b, int h,
                                  int w, int c, int r, deva_stream_t stream);
-/* Split-precision twins for a residual stream carried as fp16 (hi, lo) pairs (opt-in, DEVA_B200_RESIDUAL_LO=1): the
- * input is g + g_lo (x + x_lo), the raw result is written as (raw, raw_lo), the ReLU'd copy (an MMA operand) as hi. */
-DEVA_B200_API int deva_b200_up2_add_split(const void* g, const void* g_lo, const void* skip, void* raw, void* raw_lo,
-                                          void* relu, int b, int h, int w, int c, deva_stream_t stream);
+/* Split-precision twins for a residual stream carried as fp16 (hi, lo) pairs (the default "parity" precision plan): the
+ * input is g + g_lo (x + x_lo) [+ skip_lo, optional], the raw result is written as (raw, raw_lo) (both NULL = not
+ * wanted), the ReLU'd copy (an MMA operand) as hi, plus its remainder relu_lo when the consumer runs a second
+ * activation pass (conv split_mode 1). */
+DEVA_B200_API int deva_b200_up2_add_split(const void* g, const void* g_lo, const void* skip, const void* skip_lo,
+                                          void* raw, void* raw_lo, void* relu, void* relu_lo, int b, int h, int w, int c,
+                                          deva_stream_t stream);
 DEVA_B200_API int deva_b200_cbam_split(const void* x, const void* x_lo, const float* w1, const float* b1, const float* w2,
                                        const float* b2, const float* ws, const float* bs, float* scratch, void* raw,
-                                       void* raw_lo, void* relu, int b, int h, int w, int c, int r, deva_stream_t stream);
+                                       void* raw_lo, void* relu, void* relu_lo, int b, int h, int w, int c, int r,
+                                       deva_stream_t stream);
 /* sensory GRU gates (modules.py:145-149): values fp16 [pixels, 3c], h fp16 [pixels, c] -> out fp16 */
 DEVA_B200_API int deva_b200_gru(const void* values, const void* h, void* out, int64_t pixels, int c,
                                 deva_stream_t stream);

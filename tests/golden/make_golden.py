@@ -306,19 +306,40 @@ def golden_detections():
     core = DEVAInferenceCore(net, cfg)
     frames = sc.detect_frames()
     arrays, states = {}, []
+    # also record what the reference's detection frames see internally: the forward prediction (inference_core.py:163-167)
+    # and its argmax - random-init probabilities are near-uniform, so that argmax is ill-conditioned; the product test
+    # checks its own forward prediction against these and continues on the reference's forward mask
+    import deva.inference.inference_core as ic
+    seen = {}
+    real_merge, real_segment = ic.match_and_merge, core._segment
+
+    def merge_spy(forward_mask, *a, **k):
+        seen['fwd'] = forward_mask.clone()
+        return real_merge(forward_mask, *a, **k)
+
+    def segment_spy(*a, **k):
+        seen['prob'] = real_segment(*a, **k)
+        return seen['prob']
+
+    ic.match_and_merge, core._segment = merge_spy, segment_spy
     for t, (frame, dets) in enumerate(zip(frames, sc.DETECT_SESSION)):
+        seen.clear()
         if dets is None:
             p = core.step(frame, end=(t == len(frames) - 1))
         else:
             ids = sc.merge_masks({d[0]: d[1] for d in dets}, sc.DETECT_HW)
             infos = [ObjectInfo(d[0], category_id=d[2], isthing=d[3], score=d[4]) for d in dets]
             p = core.incorporate_detection(frame, ids, infos)
+            arrays[f'fwd_{t:02d}'] = seen['fwd'].to(torch.int16)
+            if 'prob' in seen:
+                arrays[f'fwdprob_{t:02d}'] = seen['prob'].clone()
         arrays[f'prob_{t:02d}'] = p.clone()
         mem = core.memory
         states.append({'objects': [[tt, o.id, o.poke_count, list(o.category_ids), list(o.scores)]
                                    for tt, o in core.object_manager.tmp_id_to_obj.items()],
                        'sizes': {str(b): [mem.work_mem.size(b), mem.long_mem.size(b)] for b in mem.work_mem.buckets}})
         print('  detections t', t, 'prob', tuple(p.shape), states[-1]['objects'], states[-1]['sizes'])
+    ic.match_and_merge = real_merge
     save('detections.npz', **arrays)
     json.dump({'config': cfg, 'states': states}, open(os.path.join(HERE, 'detections.json'), 'w'))
 

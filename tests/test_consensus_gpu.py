@@ -33,7 +33,7 @@ def _golden(golden_dir):
     return g, json.load(open(os.path.join(golden_dir, 'consensus.json')))
 
 
-@pytest.mark.parametrize('backend,tol', [('native', 2.5e-3), ('torch', 1e-3)])
+@pytest.mark.parametrize('backend,tol', [('native', 1e-3), ('torch', 1e-3)])
 def test_spatial_alignment_matches_reference(golden_dir, synthetic_sd, backend, tol):
     from deva.inference.consensus_associated import find_consensus_with_established_association, spatial_alignment
     from deva.inference.image_feature_store import ImageFeatureStore

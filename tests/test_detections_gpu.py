@@ -1,6 +1,5 @@
 """Semi-online session (incorporate_detection interleaved with step) against the reference-minted fixture.
-Written after the round's GPU budget was spent: the oracle side is pinned on CPU (tests/test_oracle_golden.py), this
-product-side comparison has NOT run on hardware yet - skipped unless DEVA_B200_TEST_EXPERIMENTAL=1."""
+The oracle side is pinned on CPU (tests/test_oracle_golden.py); this is the product-side comparison on the device."""
 import importlib.util
 import json
 import os
@@ -9,12 +8,10 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('DEVA_B200_TEST_EXPERIMENTAL') != '1',
-                                 reason='not yet validated on hardware; set DEVA_B200_TEST_EXPERIMENTAL=1')]
+pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('backend,tol', [('native', 2.5e-3), ('torch', 1e-3)])
+@pytest.mark.parametrize('backend,tol', [('native', 1e-3), ('torch', 1e-3)])
 def test_detection_session_matches_reference(golden_dir, synthetic_sd, backend, tol):
     from deva.inference.inference_core import DEVAInferenceCore
     from deva.inference.object_info import ObjectInfo
@@ -33,18 +30,55 @@ def test_detection_session_matches_reference(golden_dir, synthetic_sd, backend, 
     np.random.seed(42)
     core = DEVAInferenceCore(net, meta['config'])
     frames = sc.detect_frames()
-    for t, (frame, dets) in enumerate(zip(frames, sc.DETECT_SESSION)):
-        if dets is None:
-            p = core.step(frame.cuda(), end=(t == len(frames) - 1))
-        else:
-            ids = sc.merge_masks({d[0]: d[1] for d in dets}, sc.DETECT_HW).cuda()
-            infos = [ObjectInfo(d[0], category_id=d[2], isthing=d[3], score=d[4]) for d in dets]
-            p = core.incorporate_detection(frame.cuda(), ids, infos)
-        want = meta['states'][t]
-        objects = [[tt, o.id, o.poke_count, list(o.category_ids), list(o.scores)]
-                   for tt, o in core.object_manager.tmp_id_to_obj.items()]
-        assert objects == want['objects'], (t, objects, want['objects'])
-        mem = core.memory
-        sizes = {str(b): [mem.work_mem.size(b), mem.long_mem.size(b)] for b in mem.work_mem.buckets}
-        assert sizes == want['sizes'], (t, sizes, want['sizes'])
-        assert float((p.float().cpu() - g[f'prob_{t:02d}']).abs().max()) < tol, t
+    # Detection frames take argmax(forward prediction) (inference_core.py:163-167).  With random-init weights the
+    # probabilities are near-uniform, so that argmax is ill-conditioned (fp32 on 1 vs 8 threads already
+    # flips 2-6e-5 of the pixels) and a single flipped pixel changes the merged HARD mask by 2 x 16.1 in the returned
+    # logits.  So: the product's own forward prediction is checked against the reference's (recorded in the fixture) at
+    # the contract tolerance and on every confident pixel, then the session continues on the reference's forward mask.
+    import deva.inference.inference_core as ic
+    seen = {}
+    real_merge, real_segment = ic.match_and_merge, core._segment
+
+    def merge_spy(forward_mask, *a, **k):
+        seen['fwd'] = forward_mask
+        return real_merge(seen['use'].to(forward_mask.device, forward_mask.dtype), *a, **k)
+
+    def segment_spy(*a, **k):
+        seen['prob'] = real_segment(*a, **k)
+        return seen['prob']
+
+    ic.match_and_merge, core._segment = merge_spy, segment_spy
+    try:
+        for t, (frame, dets) in enumerate(zip(frames, sc.DETECT_SESSION)):
+            seen.clear()
+            if dets is None:
+                p = core.step(frame.cuda(), end=(t == len(frames) - 1))
+            else:
+                seen['use'] = g[f'fwd_{t:02d}'].long()
+                ids = sc.merge_masks({d[0]: d[1] for d in dets}, sc.DETECT_HW).cuda()
+                infos = [ObjectInfo(d[0], category_id=d[2], isthing=d[3], score=d[4]) for d in dets]
+                p = core.incorporate_detection(frame.cuda(), ids, infos)
+                ref_fwd = g[f'fwd_{t:02d}'].long()
+                assert tuple(seen['fwd'].shape) == tuple(ref_fwd.shape)
+                if f'fwdprob_{t:02d}' in g:
+                    ref_prob = g[f'fwdprob_{t:02d}']
+                    assert float((seen['prob'].float().cpu() - ref_prob).abs().max()) < tol, ('forward prediction', t)
+                    top2 = torch.topk(ref_prob, 2, dim=0)[0]
+                    confident = (top2[0] - top2[1]) > 0.05
+                    assert bool((seen['fwd'].cpu()[confident] == ref_fwd[confident]).all()), ('forward mask', t)
+                else:
+                    assert bool((seen['fwd'].cpu() == ref_fwd).all()), ('initial forward mask', t)
+            want = meta['states'][t]
+            objects = [[tt, o.id, o.poke_count, list(o.category_ids), list(o.scores)]
+                       for tt, o in core.object_manager.tmp_id_to_obj.items()]
+            assert objects == want['objects'], (t, objects, want['objects'])
+            mem = core.memory
+            sizes = {str(b): [mem.work_mem.size(b), mem.long_mem.size(b)] for b in mem.work_mem.buckets}
+            assert sizes == want['sizes'], (t, sizes, want['sizes'])
+            ref = g[f'prob_{t:02d}']
+            if dets is None:
+                assert float((p.float().cpu() - ref).abs().max()) < tol, t
+            else:  # aggregated HARD mask (network.py:33-40): +-16.1181 logits, identical given the same forward mask
+                assert float((p.float().cpu() - ref).abs().max()) < 1e-4, t
+    finally:
+        ic.match_and_merge = real_merge

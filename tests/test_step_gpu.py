@@ -19,9 +19,10 @@ def _core(cfg, sd, backend):
     return DEVAInferenceCore(net, cfg)
 
 
-# 'native': every layer on the hand-written sm_100a kernels (fp16 activations, fp32 accumulate);
-# 'torch': the same graphs through cuDNN fp32 (isolates the memory-read kernels).
-@pytest.mark.parametrize('backend,tol', [('native', 2.5e-3), ('torch', 1e-3)])
+# 'native': every layer on the hand-written sm_100a kernels (fp16 MMA operands, fp32 accumulate, the default 'parity'
+# precision plan); 'torch': the same graphs through cuDNN fp32 (isolates the memory-read kernels).
+# Both are held to north_star's 1e-3 max-abs against the fp32 reference.
+@pytest.mark.parametrize('backend,tol', [('native', 1e-3), ('torch', 1e-3)])
 def test_vos_clip_matches_reference(golden_dir, synthetic_sd, backend, tol):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False

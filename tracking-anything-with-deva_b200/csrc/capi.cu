@@ -160,7 +160,7 @@ DEVA_B200_API int deva_b200_usage(float* out, const float* use_cnt, const float*
 
 DEVA_B200_API int deva_b200_conv2d(const deva_b200_conv_desc* c, deva_stream_t stream) {
   ConvDesc d;
-  d.x = c->x; d.x2 = c->x2; d.x_lo = c->x_lo; d.batch = c->batch; d.h = c->h; d.w = c->w; d.cin_pad = c->cin_pad;
+  d.x = c->x; d.x2 = c->x2; d.x_lo = c->x_lo; d.split_mode = c->split_mode; d.batch = c->batch; d.h = c->h; d.w = c->w; d.cin_pad = c->cin_pad;
   d.w_packed = c->w_packed; d.kh = c->kh; d.kw = c->kw; d.stride = c->stride;
   d.cout = c->cout; d.cout_pad = c->cout_pad; d.nt = c->nt; d.th = c->th; d.tw = c->tw;
   d.bias = c->bias; d.res = c->res; d.res_lo = c->res_lo; d.res_broadcast = c->res_broadcast;
@@ -201,14 +201,18 @@ DEVA_B200_API int deva_b200_cbam(const void* x, const float* w1, const float* b1
                                  int w, int c, int r, deva_stream_t stream) {
   return ew_cbam(H(x), w1, b1, w2, b2, ws, bs, scratch, H(raw), H(relu), b, h, w, c, r, S(stream));
 }
-DEVA_B200_API int deva_b200_up2_add_split(const void* g, const void* g_lo, const void* skip, void* raw, void* raw_lo,
-                                          void* relu, int b, int h, int w, int c, deva_stream_t stream) {
-  return ew_up2_add_split(H(g), H(g_lo), H(skip), H(raw), H(raw_lo), H(relu), b, h, w, c, S(stream));
+DEVA_B200_API int deva_b200_up2_add_split(const void* g, const void* g_lo, const void* skip, const void* skip_lo,
+                                          void* raw, void* raw_lo, void* relu, void* relu_lo, int b, int h, int w, int c,
+                                          deva_stream_t stream) {
+  return ew_up2_add_split(H(g), H(g_lo), H(skip), H(skip_lo), H(raw), H(raw_lo), H(relu), H(relu_lo), b, h, w, c,
+                          S(stream));
 }
 DEVA_B200_API int deva_b200_cbam_split(const void* x, const void* x_lo, const float* w1, const float* b1, const float* w2,
                                        const float* b2, const float* ws, const float* bs, float* scratch, void* raw,
-                                       void* raw_lo, void* relu, int b, int h, int w, int c, int r, deva_stream_t stream) {
-  return ew_cbam_split(H(x), H(x_lo), w1, b1, w2, b2, ws, bs, scratch, H(raw), H(raw_lo), H(relu), b, h, w, c, r, S(stream));
+                                       void* raw_lo, void* relu, void* relu_lo, int b, int h, int w, int c, int r,
+                                       deva_stream_t stream) {
+  return ew_cbam_split(H(x), H(x_lo), w1, b1, w2, b2, ws, bs, scratch, H(raw), H(raw_lo), H(relu), H(relu_lo), b, h, w, c, r,
+                       S(stream));
 }
 DEVA_B200_API int deva_b200_gru(const void* values, const void* h, void* out, int64_t pixels, int c,
                                 deva_stream_t stream) {

@@ -33,6 +33,8 @@ void count_launch();  // bumps the counter read by deva_b200_launch_count()
 
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
+constexpr int kMaxDevices = 64;
+int device_slot();  // current CUDA device, clamped to [0, kMaxDevices): index of per-device one-time state
 int sm_count();  // cached multiprocessor count of the current device
 
 }  // namespace b200

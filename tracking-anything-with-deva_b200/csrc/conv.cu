@@ -519,7 +519,12 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   const int n_src = (d.x2 || d.x_lo) ? 2 : 1;
   int pass_src[3] = {0, 0, 0}, pass_w[3] = {0, 0, 0}, n_pass = 1, w_groups = 1;
   if (d.x2) { n_pass = 2; pass_src[1] = 1; pass_w[1] = 1; w_groups = 2; }          // cat[x, x2] . [W0 | W1]
-  if (d.x_lo) { n_pass = 3; pass_src[1] = 1; pass_w[1] = 0; pass_src[2] = 0; pass_w[2] = 1; w_groups = 2; }  // Xh.Wh + Xl.Wh + Xh.Wl
+  B200_REQUIRE(d.split_mode >= 0 && d.split_mode <= 2, "conv: split_mode %d unknown", d.split_mode);
+  B200_REQUIRE(d.split_mode != 1 || d.x_lo, "conv: split_mode 1 (activation hi/lo) needs x_lo");
+  B200_REQUIRE(d.split_mode != 2 || (!d.x_lo && !d.x2), "conv: split_mode 2 (weight hi/lo) takes a single input");
+  if (d.split_mode == 1) { n_pass = 2; pass_src[1] = 1; pass_w[1] = 0; }                    // Xh.W + Xl.W
+  else if (d.split_mode == 2) { n_pass = 2; pass_src[1] = 0; pass_w[1] = 1; w_groups = 2; }  // X.Wh + X.Wl
+  else if (d.x_lo) { n_pass = 3; pass_src[1] = 1; pass_w[1] = 0; pass_src[2] = 0; pass_w[2] = 1; w_groups = 2; }  // Xh.Wh + Xl.Wh + Xh.Wl
   p.taps = ktaps * n_pass;
   B200_REQUIRE(p.taps <= kMaxTaps, "conv: too many k-entries (%d)", p.taps);
   const int phases = d.stride == 1 ? 1 : 4;
@@ -599,7 +604,8 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
                  "conv: fused head needs the whole Cout (%d) in one channel tile and head_n <= %d", d.cout, kMaxHead);
     p.head_w = d.head_w; p.head_out = d.head_out; p.head_n = d.head_n;
   }
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {false};  // function attributes are per device
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(conv_kernel<false, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     B200_CUDA(cudaFuncSetAttribute(conv_kernel<true, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -633,7 +639,8 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   if (cs == 1) maps.wgt_slice = maps.wgt;
   const long long units = (long long)((p.m_tiles + cs - 1) / cs) * p.n_tiles;
   // co-resident clusters (a GPC with a leftover odd SM count strands SMs for cs = 4): ask the runtime once
-  static int max_clusters[5] = {0, 0, 0, 0, 0};
+  static int max_clusters_dev[kMaxDevices][5] = {{0}};
+  int* max_clusters = max_clusters_dev[device_slot()];
   if (cs > 1 && max_clusters[cs] == 0) {
     cudaLaunchConfig_t q{};
     q.gridDim = dim3(sm_count() / cs * cs);

@@ -11,6 +11,8 @@ struct ConvDesc {
   const void* x2;        // optional second input of the same shape: the conv sees cat[x, x2] along channels
   const void* x_lo;      // optional fp16 low-order part of x: split-precision mode, D = Xh.Wh + Xl.Wh + Xh.Wl
                          // (weights packed [cout_pad, 2 (hi, lo), taps, cin_pad]); excludes x2
+  int split_mode;        // 0: x_lo => three passes (Xh.Wh + Xl.Wh + Xh.Wl); 1: x_lo with single weights (Xh.W + Xl.W);
+                         // 2: no x_lo, weights packed (hi, lo) (X.Wh + X.Wl)
   int batch, h, w, cin_pad;
   const void* w_packed;  // fp16 [cout_pad, kh*kw*cin_pad]
   int kh, kw, stride;    // 1x1 / 3x3, stride 1 / 2, padding kh/2

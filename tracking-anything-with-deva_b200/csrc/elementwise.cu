@@ -201,8 +201,8 @@ __device__ __forceinline__ void st8_split(__half* hi, __half* lo, const float (&
 }
 __global__ void __launch_bounds__(256)
 up2_add_split_kernel(const __half* __restrict__ g, const __half* __restrict__ g_lo, const __half* __restrict__ skip,
-                     __half* __restrict__ raw, __half* __restrict__ raw_lo, __half* __restrict__ relu, int B, int h, int w,
-                     int C) {
+                     const __half* __restrict__ skip_lo, __half* __restrict__ raw, __half* __restrict__ raw_lo,
+                     __half* __restrict__ relu, __half* __restrict__ relu_lo, int B, int h, int w, int C) {
   const int H = 2 * h, W = 2 * w, C8 = C / 8;
   const int b = blockIdx.y / H, Y = blockIdx.y - b * H;
   const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.f);
@@ -235,14 +235,25 @@ up2_add_split_kernel(const __half* __restrict__ g, const __half* __restrict__ g_
 #pragma unroll
     for (int e = 0; e < 8; ++e) d[e] += l[e];
     ld8(sk + X * C + c, s_);
+    if (skip_lo) {
+      ld8(skip_lo + (long long)Y * W * C + X * C + c, l);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s_[e] += l[e];
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float top = a[e] + (bq[e] - a[e]) * wx, bot = cq[e] + (d[e] - cq[e]) * wx;
       o[e] = top + (bot - top) * wy + s_[e];
     }
     const long long off = obase + X * C + c;
-    st8_split(raw + off, raw_lo + off, o);
-    if (relu) st8(relu + off, o, true);
+    if (raw) st8_split(raw + off, raw_lo + off, o);
+    if (relu_lo) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+      st8_split(relu + off, relu_lo + off, o);
+    } else if (relu) {
+      st8(relu + off, o, true);
+    }
   }
 }
 
@@ -290,16 +301,18 @@ __global__ void area_down_plane_kernel(const float* __restrict__ x, float* __res
 // ---------------------------------------------------------------- CBAM (cbam.py:21-77)
 // per (image, channel) partial sum and max over a slice of the pixels: grid (C/128, B, kPoolSplit)
 constexpr int kPoolSplit = 16;
-__global__ void cbam_pool_kernel(const __half* __restrict__ x, float* __restrict__ psum, float* __restrict__ pmax, int HW, int C) {
+__global__ void cbam_pool_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, float* __restrict__ psum,
+                                 float* __restrict__ pmax, int HW, int C) {
   const int b = blockIdx.y, sp = blockIdx.z;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const int per = (HW + kPoolSplit - 1) / kPoolSplit;
   const int i0 = sp * per, i1 = min(HW, i0 + per);
   const __half* p = x + (long long)b * HW * C + c;
+  const __half* pl = x_lo ? x_lo + (long long)b * HW * C + c : nullptr;
   float s = 0.f, m = -CUDART_INF_F;
   for (int i = i0; i < i1; ++i) {
-    const float v = __half2float(p[(long long)i * C]);
+    const float v = __half2float(p[(long long)i * C]) + (pl ? __half2float(pl[(long long)i * C]) : 0.f);
     s += v;
     m = fmaxf(m, v);
   }
@@ -342,17 +355,18 @@ __global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __r
   }
 }
 // per pixel: max and mean over channels of x * gate -> stats [B,HW,2]; one warp per pixel
-__global__ void cbam_stats_kernel(const __half* __restrict__ x, const float* __restrict__ gate, float* __restrict__ stats,
-                                  int B, int HW, int C) {
+__global__ void cbam_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, const float* __restrict__ gate,
+                                  float* __restrict__ stats, int B, int HW, int C) {
   const long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (pix >= (long long)B * HW) return;
   const int b = (int)(pix / HW);
   const __half* p = x + pix * C;
+  const __half* pl = x_lo ? x_lo + pix * C : nullptr;
   const float* g = gate + b * C;
   float s = 0.f, m = -CUDART_INF_F;
   for (int c = lane; c < C; c += 32) {
-    const float v = __half2float(p[c]) * g[c];
+    const float v = (__half2float(p[c]) + (pl ? __half2float(pl[c]) : 0.f)) * g[c];
     s += v;
     m = fmaxf(m, v);
   }
@@ -394,7 +408,7 @@ __global__ void cbam_apply_split_kernel(const __half* __restrict__ x, const __ha
                                         const float* __restrict__ gate, const float* __restrict__ stats,
                                         const float* __restrict__ ws, const float* __restrict__ bs,
                                         __half* __restrict__ raw, __half* __restrict__ raw_lo, __half* __restrict__ relu,
-                                        int B, int H, int W, int C) {
+                                        __half* __restrict__ relu_lo, int B, int H, int W, int C) {
   const long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (pix >= (long long)B * H * W) return;
@@ -416,7 +430,12 @@ __global__ void cbam_apply_split_kernel(const __half* __restrict__ x, const __ha
     const __half hi = __float2half_rn(o);
     raw[pix * C + c] = hi;
     raw_lo[pix * C + c] = __float2half_rn(o - __half2float(hi));
-    if (relu) relu[pix * C + c] = __float2half_rn(fmaxf(o, 0.f));
+    if (relu) {
+      const float ro = fmaxf(o, 0.f);
+      const __half rh = __float2half_rn(ro);
+      relu[pix * C + c] = rh;
+      if (relu_lo) relu_lo[pix * C + c] = __float2half_rn(ro - __half2float(rh));
+    }
   }
 }
 
@@ -578,14 +597,16 @@ int ew_up2_add(const __half* g, const __half* skip, __half* raw, __half* relu, i
   B200_LAUNCH_CHECK();
   return 0;
 }
-int ew_up2_add_split(const __half* g, const __half* g_lo, const __half* skip, __half* raw, __half* raw_lo, __half* relu,
-                     int B, int h, int w, int C, cudaStream_t s) {
-  B200_REQUIRE(C % 8 == 0 && g_lo && raw && raw_lo, "up2_add_split: C %% 8 and the hi/lo tensors are required");
-  ew::up2_add_split_kernel<<<dim3(ceil_div(2 * w * (C / 8), 256 * 2), B * 2 * h), 256, 0, s>>>(g, g_lo, skip, raw, raw_lo,
-                                                                                              relu, B, h, w, C);
+int ew_up2_add_split(const __half* g, const __half* g_lo, const __half* skip, const __half* skip_lo, __half* raw,
+                     __half* raw_lo, __half* relu, __half* relu_lo, int B, int h, int w, int C, cudaStream_t s) {
+  B200_REQUIRE(C % 8 == 0 && g_lo && (raw != nullptr) == (raw_lo != nullptr) && (raw || relu) && (!relu_lo || relu),
+               "up2_add_split: C %% 8, g_lo, and raw/raw_lo (both or neither) with at least one output are required");
+  ew::up2_add_split_kernel<<<dim3(ceil_div(2 * w * (C / 8), 256 * 2), B * 2 * h), 256, 0, s>>>(
+      g, g_lo, skip, skip_lo, raw, raw_lo, relu, relu_lo, B, h, w, C);
   B200_LAUNCH_CHECK();
   return 0;
 }
+
 int ew_area_down(const __half* x, __half* y, int B, int H, int W, int C, int r, cudaStream_t s) {
   B200_REQUIRE(C % 8 == 0 && H % r == 0 && W % r == 0, "area_down: shape");
   ew::area_down_kernel<<<grid_of((long long)B * (H / r) * (W / r) * (C / 8)), 256, 0, s>>>(x, y, B, H, W, C, r);
@@ -607,36 +628,37 @@ int ew_cbam(const __half* x, const float* w1, const float* b1, const float* w2, 
   float* gate = pmax + (long long)B * ew::kPoolSplit * C;
   float* stats = gate + (long long)B * C;
   const int HW = H * W;
-  ew::cbam_pool_kernel<<<dim3(ceil_div(C, 128), B, ew::kPoolSplit), 128, 0, s>>>(x, psum, pmax, HW, C);
+  ew::cbam_pool_kernel<<<dim3(ceil_div(C, 128), B, ew::kPoolSplit), 128, 0, s>>>(x, nullptr, psum, pmax, HW, C);
   B200_LAUNCH_CHECK();
   ew::cbam_mlp_kernel<<<B, 256, (2 * C + 2 * R) * sizeof(float), s>>>(psum, pmax, HW, w1, b1, w2, b2, gate, C, R);
   B200_LAUNCH_CHECK();
   const long long warps = (long long)B * HW;
-  ew::cbam_stats_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, gate, stats, B, HW, C);
+  ew::cbam_stats_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, nullptr, gate, stats, B, HW, C);
   B200_LAUNCH_CHECK();
   ew::cbam_apply_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, gate, stats, ws, bs, raw, relu, B, H, W, C);
   B200_LAUNCH_CHECK();
   return 0;
 }
 int ew_cbam_split(const __half* x, const __half* x_lo, const float* w1, const float* b1, const float* w2, const float* b2,
-                  const float* ws, const float* bs, float* scratch, __half* raw, __half* raw_lo, __half* relu, int B, int H,
-                  int W, int C, int R, cudaStream_t s) {
-  // the gates (channel MLP, 7x7 spatial conv) are sigmoids of pooled statistics: the hi part of x is enough for them
+                  const float* ws, const float* bs, float* scratch, __half* raw, __half* raw_lo, __half* relu, __half* relu_lo,
+                  int B, int H, int W, int C, int R, cudaStream_t s) {
+  // the gate statistics are pooled over x + x_lo as well: a gate error is common to every channel of a pixel, so it
+  // does not average out in the next convolution the way independent roundings do
   B200_REQUIRE(x_lo && raw && raw_lo, "cbam_split: the hi/lo tensors are required");
   float* psum = scratch;
   float* pmax = psum + (long long)B * ew::kPoolSplit * C;
   float* gate = pmax + (long long)B * ew::kPoolSplit * C;
   float* stats = gate + (long long)B * C;
   const int HW = H * W;
-  ew::cbam_pool_kernel<<<dim3(ceil_div(C, 128), B, ew::kPoolSplit), 128, 0, s>>>(x, psum, pmax, HW, C);
+  ew::cbam_pool_kernel<<<dim3(ceil_div(C, 128), B, ew::kPoolSplit), 128, 0, s>>>(x, x_lo, psum, pmax, HW, C);
   B200_LAUNCH_CHECK();
   ew::cbam_mlp_kernel<<<B, 256, (2 * C + 2 * R) * sizeof(float), s>>>(psum, pmax, HW, w1, b1, w2, b2, gate, C, R);
   B200_LAUNCH_CHECK();
   const long long warps = (long long)B * HW;
-  ew::cbam_stats_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, gate, stats, B, HW, C);
+  ew::cbam_stats_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, x_lo, gate, stats, B, HW, C);
   B200_LAUNCH_CHECK();
-  ew::cbam_apply_split_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, x_lo, gate, stats, ws, bs, raw, raw_lo, relu, B,
-                                                                        H, W, C);
+  ew::cbam_apply_split_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, x_lo, gate, stats, ws, bs, raw, raw_lo, relu,
+                                                                        relu_lo, B, H, W, C);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -8,11 +8,11 @@ int ew_nhwc_to_nchw(const __half* src, float* dst, int B, int C, int H, int W, c
 int ew_stem_im2col(const float* src, __half* dst, __half* dst_lo, int B, int C, int H, int W, int Kp, cudaStream_t s);
 int ew_maxpool(const __half* x, const __half* x_lo, __half* y, __half* y_lo, int B, int H, int W, int C, cudaStream_t s);
 int ew_up2_add(const __half* g, const __half* skip, __half* raw, __half* relu, int B, int h, int w, int C, cudaStream_t s);
-int ew_up2_add_split(const __half* g, const __half* g_lo, const __half* skip, __half* raw, __half* raw_lo, __half* relu,
-                     int B, int h, int w, int C, cudaStream_t s);
+int ew_up2_add_split(const __half* g, const __half* g_lo, const __half* skip, const __half* skip_lo, __half* raw,
+                     __half* raw_lo, __half* relu, __half* relu_lo, int B, int h, int w, int C, cudaStream_t s);
 int ew_cbam_split(const __half* x, const __half* x_lo, const float* w1, const float* b1, const float* w2, const float* b2,
-                  const float* ws, const float* bs, float* scratch, __half* raw, __half* raw_lo, __half* relu, int B, int H,
-                  int W, int C, int R, cudaStream_t s);
+                  const float* ws, const float* bs, float* scratch, __half* raw, __half* raw_lo, __half* relu, __half* relu_lo,
+                  int B, int H, int W, int C, int R, cudaStream_t s);
 int ew_area_down(const __half* x, __half* y, int B, int H, int W, int C, int r, cudaStream_t s);
 int ew_area_down_plane(const float* x, float* y, int B, int H, int W, int r, cudaStream_t s);
 int ew_cbam(const __half* x, const float* w1, const float* b1, const float* w2, const float* b2, const float* ws,

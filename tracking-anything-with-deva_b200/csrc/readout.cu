@@ -480,7 +480,8 @@ int launch_readout(const __half* values, long long values_ld, long long values_r
     p.val_row[i] = val_row[i];
     p.out_row[i] = out_row[i];
   }
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {false};  // function attributes are per device
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(readout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
@@ -540,7 +541,8 @@ int launch_readout_sparse(const __half* values, long long values_ld, long long v
     }
   }
   B200_REQUIRE((size_t)(p.k_blocks + 1) * 4 <= 200 * 1024, "readout: window of %d slots too large for the bucket pass", n_window);
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {false};  // function attributes are per device
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(readout_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
     B200_CUDA(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

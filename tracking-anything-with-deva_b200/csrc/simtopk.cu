@@ -454,7 +454,8 @@ int launch_sim_topk(const __half* k_hi, const __half* k_lo, const float* neg_s, 
   p.neg_s = neg_s; p.bsq = bsq;
   p.part_val = reinterpret_cast<float*>(workspace);
   p.part_idx = reinterpret_cast<int*>(p.part_val + (size_t)kMaxSplit * GROUPS * kListCap * p.qpad);
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {false};  // function attributes are per device
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(simtopk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     B200_CUDA(cudaFuncSetAttribute(simtopk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -512,7 +513,8 @@ int launch_sim_dense_softmax(const __half* k_hi, const __half* k_lo, const float
   p.qpad = q_tiles * BQ;
   p.neg_s = neg_s; p.bsq = bsq;
   p.dense_out = sim_ws; p.ld_dense = ld_sim;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {false};  // function attributes are per device
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(simtopk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;

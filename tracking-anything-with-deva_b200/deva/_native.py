@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libdeva_b200.so')
-ABI_VERSION = 9
+ABI_VERSION = 10
 LIST_PITCH = 32
 MAX_GROUPS = 256
 
@@ -21,7 +21,7 @@ _lib = None
 
 class ConvDesc(ctypes.Structure):
     """Mirror of ``deva_b200_conv_desc`` (include/deva_b200.h)."""
-    _fields_ = [('x', c_void_p), ('x2', c_void_p), ('x_lo', c_void_p), ('batch', c_int32), ('h', c_int32), ('w', c_int32), ('cin_pad', c_int32),
+    _fields_ = [('x', c_void_p), ('x2', c_void_p), ('x_lo', c_void_p), ('split_mode', c_int32), ('batch', c_int32), ('h', c_int32), ('w', c_int32), ('cin_pad', c_int32),
                 ('w_packed', c_void_p), ('kh', c_int32), ('kw', c_int32), ('stride', c_int32),
                 ('cout', c_int32), ('cout_pad', c_int32), ('nt', c_int32), ('th', c_int32), ('tw', c_int32),
                 ('bias', c_void_p), ('res', c_void_p), ('res_lo', c_void_p), ('res_broadcast', c_int32),
@@ -79,10 +79,11 @@ _SIGNATURES = {
     'deva_b200_area_down_plane': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'deva_b200_cbam': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    'deva_b200_up2_add_split': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                        c_int, c_void_p]),
+    'deva_b200_up2_add_split': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_int, c_int, c_int, c_int, c_void_p]),
     'deva_b200_cbam_split': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p]),
     'deva_b200_gru': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     'deva_b200_key_tail': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'deva_b200_output_tail': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -271,8 +272,9 @@ def _p(t):
 
 def conv2d(x, batch, h, w, cin_pad, w_packed, kh, stride, cout, cout_pad, nt, th, tw, bias, x2=None, x_lo=None, res=None,
            res_lo=None, res_broadcast=False, rank1_w=None, rank1_x=None, out_raw=None, out_relu=None, out_f32=None,
-           out_raw_lo=None, out_relu_lo=None, head_w=None, head_out=None, head_n=0, gate_h=None, gate_out=None):
-    d = ConvDesc(_p(x), _p(x2), _p(x_lo), batch, h, w, cin_pad, _p(w_packed), kh, kh, stride, cout, cout_pad, nt, th, tw,
+           out_raw_lo=None, out_relu_lo=None, head_w=None, head_out=None, head_n=0, gate_h=None, gate_out=None,
+           split_mode=0):
+    d = ConvDesc(_p(x), _p(x2), _p(x_lo), split_mode, batch, h, w, cin_pad, _p(w_packed), kh, kh, stride, cout, cout_pad, nt, th, tw,
                  _p(bias), _p(res), _p(res_lo), int(res_broadcast), _p(rank1_w), _p(rank1_x), _p(out_raw), _p(out_relu),
                  _p(out_f32), _p(out_raw_lo), _p(out_relu_lo), _p(head_w), _p(head_out), head_n, _p(gate_h), _p(gate_out))
     _check(lib().deva_b200_conv2d(ctypes.byref(d), _stream()), 'conv2d')
@@ -312,15 +314,15 @@ def cbam(x, w1, b1, w2, b2, ws, bs, scratch, raw, relu, b, h, w, c, r):
                                 _ptr(raw), _ptr(relu), b, h, w, c, r, _stream()), 'cbam')
 
 
-def up2_add_split(g, g_lo, skip, raw, raw_lo, relu, b, h, w, c):
-    _check(lib().deva_b200_up2_add_split(_ptr(g), _ptr(g_lo), _ptr(skip), _ptr(raw), _ptr(raw_lo), _ptr(relu), b, h, w, c,
-                                         _stream()), 'up2_add_split')
+def up2_add_split(g, g_lo, skip, raw, raw_lo, relu, b, h, w, c, skip_lo=None, relu_lo=None):
+    _check(lib().deva_b200_up2_add_split(_ptr(g), _ptr(g_lo), _ptr(skip), _ptr(skip_lo), _ptr(raw), _ptr(raw_lo),
+                                         _ptr(relu), _ptr(relu_lo), b, h, w, c, _stream()), 'up2_add_split')
 
 
-def cbam_split(x, x_lo, w1, b1, w2, b2, ws, bs, scratch, raw, raw_lo, relu, b, h, w, c, r):
+def cbam_split(x, x_lo, w1, b1, w2, b2, ws, bs, scratch, raw, raw_lo, relu, b, h, w, c, r, relu_lo=None):
     _check(lib().deva_b200_cbam_split(_ptr(x), _ptr(x_lo), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(ws), _ptr(bs),
-                                      _ptr(scratch), _ptr(raw), _ptr(raw_lo), _ptr(relu), b, h, w, c, r, _stream()),
-           'cbam_split')
+                                      _ptr(scratch), _ptr(raw), _ptr(raw_lo), _ptr(relu), _ptr(relu_lo), b, h, w, c, r,
+                                      _stream()), 'cbam_split')
 
 
 def gru(values, h, out, pixels, c):

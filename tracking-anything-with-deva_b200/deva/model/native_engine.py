@@ -42,42 +42,61 @@ class NativeEngine:
     prefers_nhwc = True
 
     def __init__(self, sd: Dict[str, torch.Tensor]):
-        # DEVA_B200_RESIDUAL_LO=1 (opt-in, see DESIGN "precision plan"): the decoder's residual / skip stream - block
-        # outputs, CBAM residual, bilinear x2 + skip - travels as fp16 (hi, lo) pairs instead of being rounded to fp16 at
-        # every block; MMA operands stay single fp16.  Emulated gain on the golden clip: 1.98e-3 -> 1.17e-3 max |dprob|.
-        self.residual_lo = os.environ.get('DEVA_B200_RESIDUAL_LO', '0') == '1'
-        t = LayerTable(sd)
-        self.key_dim, self.value_dim = t.key_dim, t.value_dim
+        # Precision plan (DESIGN "precision plan"; tools/precision_layers.py / precision_plan.py rank the rounding sources):
+        #   'parity' (default): the decoder's residual / skip stream travels as fp16 (hi, lo) pairs, the 1x1 shortcut /
+        #       skip convolutions that consume the raw stream run in split precision (three MMA passes, they are cheap),
+        #       sensory_compress takes (hi, lo) weights, and the two 3x3 convs of the last decoder block (up_8_4, next to
+        #       the logits) take their activations as (hi, lo) pairs (two passes).  max |prob - fp32 reference| < 1e-3.
+        #   'fast': every operand and every stored activation is a single fp16 (1.7e-3 on the golden clip).
+        self.precision = os.environ.get('DEVA_B200_PRECISION', 'parity')
+        if self.precision not in ('parity', 'fast'):
+            raise RuntimeError(f"deva_b200: DEVA_B200_PRECISION must be 'parity' or 'fast', got {self.precision!r}")
+        self.parity = self.precision == 'parity'
+        self.plan_override = [tuple(item.split('=')) for item in os.environ.get('DEVA_B200_PLAN', '').split(',') if '=' in item]
+        for _, mode in self.plan_override:
+            if mode not in ('precise', 'act_lo', 'w_lo', 'single') or not self.parity:
+                raise RuntimeError('deva_b200: DEVA_B200_PLAN takes substring=precise|act_lo|w_lo|single items (parity plan only)')
         self.device = next(iter(sd.values())).device
+        # fold BatchNorm and pack the operands on the host (a few hundred tiny device launches otherwise), upload once
+        t = LayerTable({k: v.detach().to('cpu', torch.float32) if v.is_floating_point() else v.cpu() for k, v in sd.items()})
+        self.key_dim, self.value_dim = t.key_dim, t.value_dim
         L = t.layers
         P: Dict[str, ops.PackedConv] = {}
         for name, spec in L.items():
             # The key path (pixel encoder -> key projection) runs in split precision (fp16 hi/lo pairs, ~fp32
             # accuracy): the top-k read is discontinuous in the keys, and the path is < 3 % of the frame's FLOPs.
             precise = name.startswith('pixel_encoder') or name.startswith('key_proj')
+            tail = name.rsplit('.', 1)[-1]
+            if self.parity:
+                if tail in ('skip8', 'skip4', 'ds_x', 'ds_g') or name.endswith('up_16_8.out_conv.ds'):
+                    precise = True
+            act_lo = self.parity and 'up_8_4.out_conv' in name
+            w_lo = self.parity and name.endswith('.sensory_compress')
+            for pat, mode in self.plan_override:  # experiments: DEVA_B200_PLAN="substring=precise|act_lo|w_lo|single,..."
+                if pat in name and not (name.startswith('pixel_encoder') or name.startswith('key_proj')):
+                    precise, act_lo, w_lo = mode == 'precise', mode == 'act_lo', mode == 'w_lo'
             if name.endswith('.pred'):  # folded into up_8_4.c2's epilogue as a fp32 9-tap head (see decode)
-                self.pred_w = spec.weight[0].permute(1, 2, 0).reshape(9, -1).float().contiguous()  # [tap, cin]
+                self.pred_w = spec.weight[0].permute(1, 2, 0).reshape(9, -1).float().contiguous().to(self.device)  # [tap, cin]
                 self.pred_b = float(spec.bias[0])
                 continue
             if name.endswith('.stem'):
                 P[name] = ops.pack_stem(spec.weight, spec.bias, precise=True)
             elif name.endswith('.stem_img') or name.endswith('.stem_mask'):
                 P[name] = ops.pack_stem(spec.weight, spec.bias)
-            elif precise:
-                P[name] = ops.PackedConv(spec.weight, spec.bias, spec.stride, precise=True)
             elif name.endswith('.gru'):
                 P[name] = ops.PackedConv(spec.weight, spec.bias, 1, two_inputs=True, gates=True)
-            elif name.endswith('.sensory_compress'):
-                P[name] = ops.PackedConv(spec.weight, spec.bias, 1, rank1_in=spec.weight.shape[1] - 1)
-            elif name.endswith('.su.g4_conv'):
-                P[name] = ops.PackedConv(spec.weight, spec.bias, 1, rank1_in=spec.weight.shape[1] - 1)
             else:
-                P[name] = ops.PackedConv(spec.weight, spec.bias, spec.stride)
-        self.P = P
+                rank1 = spec.weight.shape[1] - 1 if (name.endswith('.sensory_compress') or name.endswith('.su.g4_conv')) else None
+                P[name] = ops.PackedConv(spec.weight, spec.bias, spec.stride, rank1_in=rank1, precise=precise,
+                                         act_lo=act_lo and not precise, w_lo=w_lo and not (precise or act_lo))
+        self.P = {k: v.to(self.device) for k, v in P.items()}
+        self.trunk_pairs = any(v.takes_lo for k, v in P.items() if k.startswith('mask_encoder.layer')) or \
+            os.environ.get('DEVA_B200_ME_PAIRS', '0') == '1'
         self.cbam = {}
         for p, c in t.cbam.items():
-            self.cbam[p] = dict(w1=c['w1'].contiguous(), b1=c['b1'].contiguous(), w2=c['w2'].contiguous(),
-                                b2=c['b2'].contiguous(), ws=c['ws'].reshape(-1).contiguous(), bs=c['bs'].contiguous())
+            self.cbam[p] = {k: v.to(self.device) for k, v in dict(
+                w1=c['w1'].contiguous(), b1=c['b1'].contiguous(), w2=c['w2'].contiguous(), b2=c['b2'].contiguous(),
+                ws=c['ws'].reshape(-1).contiguous(), bs=c['bs'].contiguous()).items()}
 
     # ------------------------------------------------------------------ key encoder (a10, a11), split precision
     def _bottleneck(self, x, q):
@@ -106,13 +125,17 @@ class NativeEngine:
                 x = self._bottleneck(x, f'{p}.{stage}.{i}')
             feats.append(x)
         f4, f8, f16 = feats
-        o1 = ops.conv_ex(f16[0], P[p + '.proj1'], x_lo=f16[1], want_raw=True, want_relu=True)
+        o1 = ops.conv_ex(f16[0], P[p + '.proj1'], x_lo=f16[1], want_raw=True, want_relu=True, want_lo=self.parity)
         o2 = ops.conv_ex(f16[0], P[p + '.proj2'], x_lo=f16[1], want_raw=True, want_lo=True)
         f16_api = _api(o1.raw)
         f16_api._b200_relu = o1.relu  # ReLU twin for the fusers' shared half (kept alive with the view)
+        f16_api._b200_lo = o1.raw_lo  # low-order parts: the shortcut / skip convs of the parity plan consume them
+        f16_api._b200_relu_lo = o1.relu_lo
+        f8_api, f4_api = _api(f8[0]), _api(f4[0])
+        f8_api._b200_lo, f4_api._b200_lo = f8[1], f4[1]
         key_feat = _api(o2.raw)
         key_feat._b200_lo = o2.raw_lo  # low-order part for the split-precision key projection
-        return (f16_api, _api(f8[0]), _api(f4[0])), key_feat
+        return (f16_api, f8_api, f4_api), key_feat
 
     def transform_key(self, feat: torch.Tensor, need_sk=True, need_ek=True):
         x = _to_nhwc(feat)
@@ -138,6 +161,14 @@ class NativeEngine:
             relu = torch.relu(raw)
         return raw, relu
 
+    @staticmethod
+    def _lo_of(x_api: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+        """Low-order part riding on an API view (zeros when the tensor came from elsewhere, e.g. a user's own features)."""
+        lo = getattr(x_api, '_b200_lo', None)
+        if lo is None or lo.shape != like.shape:
+            lo = torch.zeros_like(like)
+        return lo
+
     def _fuse(self, p, x_raw, x_relu, g_raw, g_relu):
         """GroupFeatureFusionBlock (group_modules.py:133-152): returns the raw block output [K,h,w,C]."""
         P = self.P
@@ -150,18 +181,38 @@ class NativeEngine:
         y = ops.conv(gr_relu, P[p + '.b2.c1'], want_relu=True)
         return ops.conv(y, P[p + '.b2.c2'], res=gr_raw, want_raw=True)
 
-    def _fuse_split(self, p, x_raw, x_relu, g_raw, g_relu, g_raw_lo=None):
-        """_fuse with the block outputs carried as (hi, lo): returns (raw, raw_lo)."""
-        P = self.P
-        sx = ops.conv(x_relu, P[p + '.b1.c1_x'], want_raw=True)
-        dx = ops.conv(x_raw, P[p + '.b1.ds_x'], want_raw=True)
-        y = ops.conv(g_relu, P[p + '.b1.c1_g'], res=sx, want_relu=True)
-        short = ops.conv_ex(g_raw, P[p + '.b1.ds_g'], res=dx, want_raw=True, want_lo=True)
-        g = ops.conv_ex(y, P[p + '.b1.c2'], res=short.raw, res_lo=short.raw_lo, want_raw=True, want_lo=True)
-        gr_raw, gr_lo, gr_relu = ops.cbam_residual_split(g.raw, g.raw_lo, self.cbam[p])
-        y = ops.conv(gr_relu, P[p + '.b2.c1'], want_relu=True)
-        out = ops.conv_ex(y, P[p + '.b2.c2'], res=gr_raw, res_lo=gr_lo, want_raw=True, want_lo=True)
+    def _C(self, name, x, lo=None, **kw) -> ops.ConvOut:
+        """Conv `name` on (x, lo): the low-order part is consumed only when the layer's precision mode takes it."""
+        pc = self.P[name]
+        if pc.takes_lo:
+            return ops.conv_ex(x, pc, x_lo=lo if lo is not None else torch.zeros_like(x), **kw)
+        return ops.conv_ex(x, pc, **kw)
+
+    def _tl(self, name) -> bool:
+        return self.P[name].takes_lo
+
+    def _fuse_split(self, p, X, g_raw, g_lo, g_relu, g_relu_lo=None):
+        """_fuse of the parity plan: the block's residual stream (shortcut, block outputs, CBAM residual) is carried as
+        (hi, lo) pairs and the two 1x1 shortcut convs - they map the raw stream straight onto the output - run in split
+        precision; every MMA operand gets its low-order part when its layer's mode takes one.  X = the shared feature
+        (raw, raw_lo, relu, relu_lo).  Returns (raw, raw_lo)."""
+        x_raw, x_lo, x_relu, x_relu_lo = X
+        q = p + '.b1'
+        sx = self._C(q + '.c1_x', x_relu, x_relu_lo, want_raw=True, want_lo=True)
+        dx = self._C(q + '.ds_x', x_raw, x_lo, want_raw=True, want_lo=True)
+        y = self._C(q + '.c1_g', g_relu, g_relu_lo, res=sx.raw, res_lo=sx.raw_lo, want_relu=True, want_lo=self._tl(q + '.c2'))
+        short = self._C(q + '.ds_g', g_raw, g_lo, res=dx.raw, res_lo=dx.raw_lo, want_raw=True, want_lo=True)
+        g = self._C(q + '.c2', y.relu, y.relu_lo, res=short.raw, res_lo=short.raw_lo, want_raw=True, want_lo=True)
+        gr_raw, gr_lo, gr_relu, gr_relu_lo = ops.cbam_residual_split(g.raw, g.raw_lo, self.cbam[p],
+                                                                     want_relu_lo=self._tl(p + '.b2.c1'))
+        y = self._C(p + '.b2.c1', gr_relu, gr_relu_lo, want_relu=True, want_lo=self._tl(p + '.b2.c2'))
+        out = self._C(p + '.b2.c2', y.relu, y.relu_lo, res=gr_raw, res_lo=gr_lo, want_raw=True, want_lo=True)
         return out.raw, out.raw_lo
+
+    def _shared_quad(self, x_api: torch.Tensor):
+        raw, relu = self._shared_pair(x_api)
+        relu_lo = getattr(x_api, '_b200_relu_lo', None)
+        return raw, self._lo_of(x_api, raw), relu, relu_lo
 
     def _gru(self, key, g, h):
         # 3x3 conv over cat[g, h] -> (forget, update, new) gates -> h' (modules.py:145-149,163-167), one kernel:
@@ -175,6 +226,17 @@ class NativeEngine:
         short = ops.conv(x, P[q + '.ds'], want_raw=True) if (q + '.ds') in P else x
         return ops.conv(y, P[q + '.c2'], res=short, want_relu=True)
 
+    def _basic_pair(self, x, lo, q):
+        """BasicBlock on a post-ReLU (hi, lo) pair (parity plan): returns the output pair."""
+        y = self._C(q + '.c1', x, lo, want_relu=True, want_lo=self._tl(q + '.c2'))
+        if (q + '.ds') in self.P:
+            s_ = self._C(q + '.ds', x, lo, want_raw=True, want_lo=True)
+            short, short_lo = s_.raw, s_.raw_lo
+        else:
+            short, short_lo = x, lo
+        o = self._C(q + '.c2', y.relu, y.relu_lo, res=short, res_lo=short_lo, want_relu=True, want_lo=True)
+        return o.relu, o.relu_lo
+
     def encode_mask(self, image, ms_features, sensory, masks, deep_update=True, chunk_size=-1):
         """image [1,3,H,W], sensory [1,K,C,h,w], masks [1,K,H,W] -> (value, sensory') as API views."""
         P, p = self.P, 'mask_encoder'
@@ -182,17 +244,39 @@ class NativeEngine:
         step = k if chunk_size < 1 or chunk_size >= k else chunk_size
         img_pc, msk_pc = P[p + '.stem_img'], P[p + '.stem_mask']
         shared = ops.conv(ops.stem_columns(image.float(), img_pc.cin_pad), img_pc, want_raw=True)
-        x_raw, x_relu = self._shared_pair(ms_features[0])
+        if self.parity:
+            X = self._shared_quad(ms_features[0])
+        else:
+            x_raw, x_relu = self._shared_pair(ms_features[0])
         h_all = _to_nhwc(sensory[0])
         planes = masks[0].float().contiguous().unsqueeze(1)  # [K,1,H,W]
         values, hiddens = [], []
         for i in range(0, k, step):
-            x = ops.conv(ops.stem_columns(planes[i:i + step], msk_pc.cin_pad), msk_pc, res=shared, want_relu=True)
-            x = ops.maxpool(x)  # ReLU and max-pool commute (quirk Q6)
-            for stage in ('layer1', 'layer2', 'layer3'):
-                for b in range(2):
-                    x = self._basic(x, f'{p}.{stage}.{b}')
-            g16 = self._fuse(p + '.fuser', x_raw, x_relu, x, x)
+            cols = ops.stem_columns(planes[i:i + step], msk_pc.cin_pad)
+            if self.parity and self.trunk_pairs:  # the whole ResNet-18 trunk on (hi, lo) pairs (plan experiments)
+                o = ops.conv_ex(cols, msk_pc, res=shared, want_relu=True, want_lo=True)
+                x, lo = ops.maxpool(o.relu, o.relu_lo)  # ReLU and max-pool commute (quirk Q6)
+                for stage in ('layer1', 'layer2', 'layer3'):
+                    for b in range(2):
+                        x, lo = self._basic_pair(x, lo, f'{p}.{stage}.{b}')
+                g16, _ = self._fuse_split(p + '.fuser', X, x, lo, x, lo)
+            elif self.parity:  # single-fp16 trunk; its last block hands the fuser a (hi, lo) pair
+                x = ops.conv(cols, msk_pc, res=shared, want_relu=True)
+                x = ops.maxpool(x)
+                for stage in ('layer1', 'layer2', 'layer3'):
+                    for b in range(2):
+                        if stage == 'layer3' and b == 1:
+                            x, lo = self._basic_pair(x, None, f'{p}.{stage}.{b}')
+                        else:
+                            x = self._basic(x, f'{p}.{stage}.{b}')
+                g16, _ = self._fuse_split(p + '.fuser', X, x, lo, x, lo)
+            else:
+                x = ops.conv(cols, msk_pc, res=shared, want_relu=True)
+                x = ops.maxpool(x)  # ReLU and max-pool commute (quirk Q6)
+                for stage in ('layer1', 'layer2', 'layer3'):
+                    for b in range(2):
+                        x = self._basic(x, f'{p}.{stage}.{b}')
+                g16 = self._fuse(p + '.fuser', x_raw, x_relu, x, x)
             values.append(g16)
             if deep_update:
                 hiddens.append(self._gru(p + '.gru', g16, h_all[i:i + step].contiguous()))
@@ -211,9 +295,16 @@ class NativeEngine:
         f16, f8, f4 = ms_features
         k = readout.shape[1]
         step = k if chunk_size < 1 or chunk_size >= k else chunk_size
-        x_raw, x_relu = self._shared_pair(f16)
-        skip8 = ops.conv(_to_nhwc(f8), P[p + '.skip8'], want_raw=True)
-        skip4 = ops.conv(_to_nhwc(f4), P[p + '.skip4'], want_raw=True)
+        f8n, f4n = _to_nhwc(f8), _to_nhwc(f4)
+        if self.parity:
+            X = self._shared_quad(f16)
+            s8 = self._C(p + '.skip8', f8n, self._lo_of(f8, f8n), want_raw=True, want_lo=True)
+            s4 = self._C(p + '.skip4', f4n, self._lo_of(f4, f4n), want_raw=True, want_lo=True)
+            skip8, skip8_lo, skip4, skip4_lo = s8.raw, s8.raw_lo, s4.raw, s4.raw_lo
+        else:
+            x_raw, x_relu = self._shared_pair(f16)
+            skip8 = ops.conv(f8n, P[p + '.skip8'], want_raw=True)
+            skip4 = ops.conv(f4n, P[p + '.skip4'], want_raw=True)
         ro_all = _to_nhwc(readout[0])
         h_all = _to_nhwc(sensory[0])
         hh, ww = ro_all.shape[1:3]
@@ -223,19 +314,26 @@ class NativeEngine:
         logits_all, hiddens = [], []
         for i in range(0, k, step):
             h = h_all[i:i + step].contiguous()
-            p16_raw, p16_relu = ops.conv(h, P[p + '.sensory_compress'], rank1_x=last[i:i + step].contiguous(),
-                                         res=ro_all[i:i + step].contiguous(), want_raw=True, want_relu=True)
-            g4_lo = None
-            if self.residual_lo:
-                p16, p16_lo = self._fuse_split(p + '.fuser', x_raw, x_relu, p16_raw, p16_relu)
-                g8_raw, g8_lo, g8_relu = ops.up2_add_split(p16, p16_lo, skip8)
+            if self.parity:
+                tl = self._tl
+                c16 = self._C(p + '.sensory_compress', h, rank1_x=last[i:i + step].contiguous(),
+                              res=ro_all[i:i + step].contiguous(), want_raw=True, want_relu=True, want_lo=True)
+                p16, p16_lo = self._fuse_split(p + '.fuser', X, c16.raw, c16.raw_lo, c16.relu, c16.relu_lo)
                 q = p + '.up_16_8.out_conv'
-                y = ops.conv(g8_relu, P[q + '.c1'], want_relu=True)
-                short = ops.conv_ex(g8_raw, P[q + '.ds'], want_raw=True, want_lo=True)
-                o8 = ops.conv_ex(y, P[q + '.c2'], res=short.raw, res_lo=short.raw_lo, want_raw=True, want_lo=True)
+                g8_raw, g8_lo, g8_relu, g8_relu_lo = ops.up2_add_split(p16, p16_lo, skip8, skip8_lo, want_relu_lo=tl(q + '.c1'))
+                y = self._C(q + '.c1', g8_relu, g8_relu_lo, want_relu=True, want_lo=tl(q + '.c2'))
+                short = self._C(q + '.ds', g8_raw, g8_lo, want_raw=True, want_lo=True)
+                o8 = self._C(q + '.c2', y.relu, y.relu_lo, res=short.raw, res_lo=short.raw_lo, want_raw=True, want_lo=True)
                 p8 = o8.raw
-                g4_raw, g4_lo, g4_relu = ops.up2_add_split(p8, o8.raw_lo, skip4)
+                q = p + '.up_8_4.out_conv'
+                g4_raw, g4_lo, g4_relu, g4_relu_lo = ops.up2_add_split(p8, o8.raw_lo, skip4, skip4_lo, want_relu_lo=tl(q + '.c1'))
+                y4 = self._C(q + '.c1', g4_relu, g4_relu_lo, want_relu=True, want_lo=tl(q + '.c2'))
+                # p4 = c2(...) + g4; the logit conv pred(relu(p4)) (big_modules.py:189-190) is folded in: the epilogue
+                # emits the 9 per-tap dot products in fp32, a 3x3 gather finishes the convolution.
+                o4 = self._C(q + '.c2', y4.relu, y4.relu_lo, res=g4_raw, res_lo=g4_lo, want_raw=True, head_w=self.pred_w)
             else:
+                p16_raw, p16_relu = ops.conv(h, P[p + '.sensory_compress'], rank1_x=last[i:i + step].contiguous(),
+                                             res=ro_all[i:i + step].contiguous(), want_raw=True, want_relu=True)
                 p16 = self._fuse(p + '.fuser', x_raw, x_relu, p16_raw, p16_relu)
                 g8_raw, g8_relu = ops.up2_add(p16, skip8)
                 q = p + '.up_16_8.out_conv'
@@ -243,11 +341,11 @@ class NativeEngine:
                 short = ops.conv(g8_raw, P[q + '.ds'], want_raw=True)
                 p8 = ops.conv(y, P[q + '.c2'], res=short, want_raw=True)
                 g4_raw, g4_relu = ops.up2_add(p8, skip4)
-            q = p + '.up_8_4.out_conv'
-            y = ops.conv(g4_relu, P[q + '.c1'], want_relu=True)
-            # p4 = c2(...) + g4; the logit conv pred(relu(p4)) (big_modules.py:189-190) is folded in: the epilogue
-            # emits the 9 per-tap dot products in fp32, a 3x3 gather finishes the convolution.
-            o4 = ops.conv_ex(y, P[q + '.c2'], res=g4_raw, res_lo=g4_lo, want_raw=True, head_w=self.pred_w)
+                q = p + '.up_8_4.out_conv'
+                y = ops.conv(g4_relu, P[q + '.c1'], want_relu=True)
+                # p4 = c2(...) + g4; the logit conv pred(relu(p4)) (big_modules.py:189-190) is folded in: the epilogue
+                # emits the 9 per-tap dot products in fp32, a 3x3 gather finishes the convolution.
+                o4 = ops.conv_ex(y, P[q + '.c2'], res=g4_raw, want_raw=True, head_w=self.pred_w)
             p4_raw = o4.raw
             logits = torch.empty(o4.head.shape[0], 4 * hh, 4 * ww, 1, dtype=torch.float32, device=o4.head.device)
             nat.head_gather3x3(o4.head, logits, self.pred_b, o4.head.shape[0], 4 * hh, 4 * ww)

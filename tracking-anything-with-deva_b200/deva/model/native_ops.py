@@ -9,6 +9,8 @@ import torch
 
 from deva import _native as nat
 
+PROFILE = None  # set to a list by bench.py to collect (start event, end event, algorithmic FLOPs, MMA passes) per conv
+
 _TILES = ((1, 128), (2, 64), (4, 32), (8, 16), (16, 8), (32, 4))
 
 
@@ -30,11 +32,14 @@ class PackedConv:
     """One convolution ready for ``deva_b200_conv2d``."""
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int,
                  rank1_in: Optional[int] = None, two_inputs: bool = False, precise: bool = False,
-                 gates: bool = False):
+                 gates: bool = False, act_lo: bool = False, w_lo: bool = False):
         """weight [Cout, Cin, k, k] fp32 (BN folded); if ``rank1_in`` is given, that input channel is split
         off as a rank-1 term (out += w[:, rank1_in] * x1) - used for the '+1' mask / logit channels.
         ``gates``: Cout = [forget | update | new] x C of a sensory updater; rows are regrouped so that every
-        192-channel tile holds the three gates of 64 hidden channels and the conv epilogue applies the update."""
+        192-channel tile holds the three gates of 64 hidden channels and the conv epilogue applies the update.
+        Precision modes (exclusive): ``precise`` = inputs (hi, lo) x weights (hi, lo), three MMA passes, ~fp32;
+        ``act_lo`` = inputs (hi, lo) x single fp16 weights, two passes (no activation-operand rounding);
+        ``w_lo`` = single fp16 input x weights (hi, lo), two passes (no weight rounding)."""
         cout, cin, kh, kw = weight.shape
         self.gates = gates
         if gates:
@@ -54,7 +59,10 @@ class PackedConv:
             cin -= 1
         self.two_inputs = two_inputs
         self.precise = precise  # split precision: weights stored as fp16 (hi, lo), inputs arrive as (hi, lo)
-        assert not (two_inputs and precise)
+        self.act_lo, self.w_lo = act_lo, w_lo
+        assert int(precise) + int(act_lo) + int(w_lo) <= 1 and not (two_inputs and (precise or act_lo or w_lo))
+        self.split_mode = 1 if act_lo else (2 if w_lo else 0)
+        self.takes_lo = precise or act_lo
         if two_inputs:  # the layer consumes cat[x, x2]: pack [cout, source, tap, cin/2]
             assert cin % 128 == 0 and stride == 1
             cin //= 2
@@ -74,7 +82,7 @@ class PackedConv:
         for s_ in range(nsrc):
             part = weight[:, s_ * cin:(s_ + 1) * cin]
             w[:cout, s_, :, :cin] = part.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
-        if precise:
+        if precise or w_lo:
             hi = w.half()
             lo = (w - hi.float()).half()
             w = torch.cat([hi.float(), lo.float()], 1)
@@ -86,6 +94,14 @@ class PackedConv:
         if rank1_in is not None:
             self.rank1_w = torch.zeros(self.cout_pad, dtype=torch.float32, device=dev)
             self.rank1_w[:cout] = r1
+
+    def to(self, device) -> 'PackedConv':
+        """Packing runs where the checkpoint lives (the engine packs on the host); this uploads the packed operands."""
+        self.w_packed = self.w_packed.to(device)
+        self.bias = self.bias.to(device)
+        if self.rank1_w is not None:
+            self.rank1_w = self.rank1_w.to(device)
+        return self
 
     def out_hw(self, h: int, w: int) -> Tuple[int, int]:
         p = self.k // 2
@@ -106,7 +122,7 @@ def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = Non
             gate_h: Optional[torch.Tensor] = None) -> ConvOut:
     """x fp16 NHWC [B,H,W,cin_pad] (+ x2: implicit channel concat, or + x_lo: split precision) -> ConvOut."""
     assert x.dtype == torch.float16 and x.is_contiguous() and x.shape[-1] == pc.cin_pad, (x.shape, pc.cin_pad)
-    assert (x2 is not None) == pc.two_inputs and (x_lo is not None) == pc.precise
+    assert (x2 is not None) == pc.two_inputs and (x_lo is not None) == pc.takes_lo, (x_lo is None, pc.takes_lo)
     for other in (x2, x_lo):
         if other is not None:
             assert other.dtype == torch.float16 and other.is_contiguous() and other.shape == x.shape
@@ -145,11 +161,18 @@ def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = Non
         assert gate_h.dtype == torch.float16 and gate_h.is_contiguous() and gate_h.shape == (b, ho, wo, pc.cout // 3)
         assert not (want_raw or want_relu or want_f32 or res is not None or head_w is not None)
         o.hidden = torch.empty_like(gate_h)
+    if PROFILE is not None:  # bench.py's conv-roofline pass: CUDA events around the launch + algorithmic FLOPs
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     nat.conv2d(x, b, h, w, pc.cin_pad, pc.w_packed, pc.k, pc.stride, pc.cout, pc.cout_pad, pc.nt, th, tw, pc.bias,
                x2=x2, x_lo=x_lo, res=res, res_lo=res_lo, res_broadcast=res_b, rank1_w=pc.rank1_w,
                rank1_x=rank1_x if pc.rank1_w is not None else None, out_raw=o.raw, out_relu=o.relu, out_f32=o.f32,
                out_raw_lo=o.raw_lo, out_relu_lo=o.relu_lo, head_w=head_w, head_out=o.head, head_n=head_n,
-               gate_h=gate_h, gate_out=o.hidden)
+               gate_h=gate_h, gate_out=o.hidden, split_mode=pc.split_mode)
+    if PROFILE is not None:
+        ev1.record()
+        flops = 2.0 * b * ho * wo * pc.cout * pc.k * pc.k * pc.cin * (2 if pc.two_inputs else 1)
+        PROFILE.append((ev0, ev1, flops, 3 if pc.precise else (2 if (pc.act_lo or pc.w_lo) else 1)))
     return o
 
 
@@ -197,14 +220,19 @@ def up2_add(g: torch.Tensor, skip: torch.Tensor, want_raw=True, want_relu=True):
     return raw, relu
 
 
-def up2_add_split(g: torch.Tensor, g_lo: torch.Tensor, skip: torch.Tensor):
-    """(g + g_lo) bilinear x2 + skip -> (raw, raw_lo, relu): the residual stream stays a fp16 hi/lo pair."""
+def up2_add_split(g: torch.Tensor, g_lo: torch.Tensor, skip: torch.Tensor, skip_lo: Optional[torch.Tensor] = None,
+                  want_raw: bool = True, want_relu_lo: bool = False):
+    """(g + g_lo) bilinear x2 + (skip + skip_lo) -> (raw, raw_lo, relu, relu_lo): the residual stream stays a fp16
+    hi/lo pair; relu_lo only when the consumer runs a second activation pass."""
     b, h, w, c = g.shape
     assert skip.shape == (1, 2 * h, 2 * w, c) and g_lo.shape == g.shape
-    raw = torch.empty(b, 2 * h, 2 * w, c, dtype=torch.float16, device=g.device)
-    raw_lo, relu = torch.empty_like(raw), torch.empty_like(raw)
-    nat.up2_add_split(g, g_lo, skip, raw, raw_lo, relu, b, h, w, c)
-    return raw, raw_lo, relu
+    assert skip_lo is None or skip_lo.shape == skip.shape
+    new = lambda: torch.empty(b, 2 * h, 2 * w, c, dtype=torch.float16, device=g.device)  # noqa: E731
+    raw, raw_lo = (new(), new()) if want_raw else (None, None)
+    relu = new()
+    relu_lo = new() if want_relu_lo else None
+    nat.up2_add_split(g, g_lo, skip, raw, raw_lo, relu, b, h, w, c, skip_lo=skip_lo, relu_lo=relu_lo)
+    return raw, raw_lo, relu, relu_lo
 
 
 def area_down(x: torch.Tensor, r: int) -> torch.Tensor:
@@ -234,15 +262,16 @@ def cbam_residual(x: torch.Tensor, params: dict, want_raw=True, want_relu=True):
     return raw, relu
 
 
-def cbam_residual_split(x: torch.Tensor, x_lo: torch.Tensor, params: dict):
-    """(x + x_lo) + CBAM(x) -> (raw, raw_lo, relu)."""
+def cbam_residual_split(x: torch.Tensor, x_lo: torch.Tensor, params: dict, want_relu_lo: bool = False):
+    """(x + x_lo) + CBAM(x + x_lo) -> (raw, raw_lo, relu, relu_lo)."""
     b, h, w, c = x.shape
     r = params['w1'].shape[0]
     scratch = torch.empty(33 * b * c + 2 * b * h * w, dtype=torch.float32, device=x.device)
     raw, raw_lo, relu = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    relu_lo = torch.empty_like(x) if want_relu_lo else None
     nat.cbam_split(x, x_lo, params['w1'], params['b1'], params['w2'], params['b2'], params['ws'], params['bs'], scratch,
-                   raw, raw_lo, relu, b, h, w, c, r)
-    return raw, raw_lo, relu
+                   raw, raw_lo, relu, b, h, w, c, r, relu_lo=relu_lo)
+    return raw, raw_lo, relu, relu_lo
 
 
 def gru(values: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
