@@ -194,6 +194,10 @@ typedef struct deva_b200_conv_desc {
    * gate_out = sigmoid(f) * gate_h * (1 - sigmoid(u)) + sigmoid(u) * tanh(n), evaluated on the fp32 accumulators. */
   const void* gate_h;   /* fp16 NHWC [batch, ho, wo, cout/3] previous hidden state */
   void* gate_out;       /* fp16 NHWC [batch, ho, wo, cout/3] new hidden state */
+  int32_t ksplit;       /* > 1: split the K loop into that many chains (fp32 output only): out_f32 then holds
+                         * ceil(k_iters / ceil(k_iters / ksplit)) partial sums [part, batch, ho, wo, cout] (bias in part 0)
+                         * for the consumer to add in fp32.  The tensor core's accumulator rounds toward zero at every
+                         * accumulation step; short chains keep a split-precision convolution at fp32 accuracy. */
 } deva_b200_conv_desc;
 /* nn.Conv2d + folded BatchNorm (+ residual, + ReLU) as in deva/model/resnet.py:46-114, group_modules.py:41-67,
  * modules.py:22-39; `desc` is a HOST struct. */
@@ -233,9 +237,16 @@ DEVA_B200_API int deva_b200_cbam_split(const void* x, const void* x_lo, const fl
 /* sensory GRU gates (modules.py:145-149): values fp16 [pixels, 3c], h fp16 [pixels, c] -> out fp16 */
 DEVA_B200_API int deva_b200_gru(const void* values, const void* h, void* out, int64_t pixels, int c,
                                 deva_stream_t stream);
-/* key projection tail (modules.py:73-78): y fp32 [q, ld] = [key | d | e] -> key [q,ck], shrinkage [q], selection [q,ck] */
-DEVA_B200_API int deva_b200_key_tail(const float* y, int ld, int q, int ck, float* key, float* shrinkage,
-                                     float* selection, deva_stream_t stream);
+/* Finish of a split-K convolution (deva_b200_conv2d with ksplit > 1): out = sum of the n_parts fp32 partial sums
+ * (part_stride elements apart, bias in part 0) + optional fp16 residual (res + res_lo), written as fp16 raw / ReLU'd
+ * tensors, each optionally as a (hi, lo) pair.  n = elements per part (multiple of 8). */
+DEVA_B200_API int deva_b200_sum_parts(const float* parts, int n_parts, int64_t part_stride, const void* res,
+                                      const void* res_lo, void* raw, void* raw_lo, void* relu, void* relu_lo, int64_t n,
+                                      deva_stream_t stream);
+/* key projection tail (modules.py:73-78): y fp32 [q, ld] = [key | d | e], given as n_parts partial sums part_stride
+ * elements apart (deva_b200_conv2d's ksplit) -> key [q,ck], shrinkage [q] = d^2 + 1, selection [q,ck] = sigmoid(e) */
+DEVA_B200_API int deva_b200_key_tail(const float* y, int ld, int q, int ck, int n_parts, int64_t part_stride, float* key,
+                                     float* shrinkage, float* selection, deva_stream_t stream);
 /* sigmoid -> aggregate -> bilinear x4 -> softmax (network.py:33-40,144-168): logits fp32 [k,h,w] ->
  * prob fp32 [(k+1),4h,4w] (and optionally the up-sampled logits); agg: fp32 scratch [(k+1),h,w] */
 DEVA_B200_API int deva_b200_output_tail(const float* logits, float* agg, float* prob, float* logits_out, int k, int h,

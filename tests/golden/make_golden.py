@@ -344,7 +344,50 @@ def golden_detections():
     json.dump({'config': cfg, 'states': states}, open(os.path.join(HERE, 'detections.json'), 'w'))
 
 
+def golden_config1():
+    """BASELINE configs[0]: the reference's own example clip (example/vos/bmx-trees, 4 frames 854x480, first-frame ids
+    {1, 2}) through DEVAInferenceCore.step exactly as evaluation/eval_vos.py:110-198 drives it (generic dataset, size 480,
+    no flip): frames decoded and normalised like deva/inference/data/video_reader.py:146-170, per-video config like
+    eval_vos.py:124-128.  Stored: the decoded uint8 frames, the annotation, and per frame the reference's id map, the
+    confident-pixel mask (top-2 margin > 0.05, bit-packed) and the probabilities on a stride-4 lattice (fp16 storage of
+    fp32 values is NOT used: kept fp32 so the 1e-3 contract can be checked)."""
+    from PIL import Image
+    from torchvision import transforms
+    root = '/root/reference/example/vos'
+    vid = 'bmx-trees'
+    names = sorted(os.listdir(os.path.join(root, 'JPEGImages', vid)))
+    norm = transforms.Compose([transforms.ToTensor(),
+                               transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])  # dataset/utils.py
+    frames_u8 = np.stack([np.array(Image.open(os.path.join(root, 'JPEGImages', vid, n)).convert('RGB')) for n in names])
+    mask0 = np.array(Image.open(os.path.join(root, 'Annotations', vid, names[0][:-4] + '.png')))
+    labels = [int(v) for v in np.unique(mask0) if v != 0]
+    cfg = dict(CFG)
+    vid_length = len(names)
+    cfg['enable_long_term_count_usage'] = bool(cfg['enable_long_term'] and (
+        vid_length / (cfg['max_mid_term_frames'] - cfg['min_mid_term_frames']) * cfg['num_prototypes']) >= cfg['max_long_term_elements'])
+    net = DEVA(cfg).eval()
+    net.load_weights(param_spec.synthetic_state_dict(seed=1))
+    np.random.seed(42)
+    core = DEVAInferenceCore(net, cfg)
+    arrays = dict(frames_u8=frames_u8, mask0=mask0.astype(np.uint8))
+    for t in range(vid_length):
+        image = norm(Image.fromarray(frames_u8[t]))
+        mask = torch.from_numpy(mask0.astype(np.int64)) if t == 0 else None
+        prob = core.step(image, mask, labels if t == 0 else None, end=(t == vid_length - 1))
+        ids = core.object_manager.tmp_to_obj_cls(torch.argmax(prob, dim=0))
+        top2 = torch.topk(prob, 2, dim=0)[0]
+        arrays[f'ids_{t}'] = ids.numpy().astype(np.uint8)
+        arrays[f'confident_{t}'] = np.packbits(((top2[0] - top2[1]) > 0.05).numpy())
+        arrays[f'prob_lattice_{t}'] = prob[:, 1::4, 2::4].contiguous().numpy()
+        print('  config1 t', t, 'prob', tuple(prob.shape), 'ids', np.unique(arrays[f'ids_{t}']).tolist(),
+              'confident', float(((top2[0] - top2[1]) > 0.05).float().mean()))
+    save('config1_vos.npz', **arrays)
+    json.dump({'config': cfg, 'labels': labels, 'frames': names, 'video': vid},
+              open(os.path.join(HERE, 'config1_vos.json'), 'w'))
+
+
 if __name__ == '__main__':
+    golden_config1()
     golden_spec()
     golden_memory_read()
     golden_bank_trace()

@@ -123,3 +123,28 @@ def test_fast_plan_is_still_available(golden_dir, synthetic_sd, monkeypatch):
         worst = max(worst, float((p.cpu() - g[f'prob_{t:02d}']).abs().max()))
     print('fast plan: max |prob - reference| =', worst)
     assert worst < 2.5e-3, worst
+
+
+@pytest.mark.parametrize('ksplit', [1, 4, 8])
+def test_conv_split_k_partial_sums(ksplit):
+    """ksplit: the K loop runs as short accumulation chains whose fp32 partial sums the consumer adds - the result
+    must equal the convolution (and, for a deep split-precision K loop, be closer to fp64 than one long chain: the tensor
+    core's accumulator rounds toward zero at every step)."""
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(31)
+    b, h, w, cin, cout, k = 1, 30, 43, 512, 129, 3   # the key projection's shape: ragged Cout, one channel tile
+    x = torch.randn(b, cin, h, w, device='cuda', generator=g)
+    wgt = torch.randn(cout, cin, k, k, device='cuda', generator=g) / (cin * k * k)**0.5
+    bias = torch.randn(cout, device='cuda', generator=g)
+    pc = ops.PackedConv(wgt, bias, 1, precise=True)
+    xh, xl = _split(_nhwc(x))
+    ref = F.conv2d(x.double(), wgt.double(), bias.double(), padding=1)
+    o = ops.conv_ex(xh, pc, x_lo=xl, want_f32=True, ksplit=ksplit)
+    torch.cuda.synchronize()
+    parts = o.f32 if ksplit > 1 else o.f32.unsqueeze(0)
+    assert parts.shape[0] == max(ksplit, 1)
+    got = parts.double().sum(0).permute(0, 3, 1, 2)
+    scale = float(ref.abs().max())
+    err = float((got - ref).abs().max()) / scale
+    print(f'split-K {ksplit}: max rel err {err:.2e}')
+    assert err < (5e-5 if ksplit == 1 else 5e-6), err  # one chain: the accumulator's round-toward-zero shows

@@ -28,11 +28,52 @@ DEFAULT_PLANS = [
     ('+ fuser act_lo', 'mask_decoder.fuser.b1.c=act_lo,mask_decoder.fuser.b2=act_lo'),
     ('+ whole decoder precise (GRU single)', 'mask_decoder=precise'),
     ('+ mask encoder precise (GRU single)', 'mask_encoder=precise'),
-    ('+ decoder and mask encoder precise', 'mask_decoder=precise,mask_encoder=precise'),
+    ('parity, key projection in fp32 ATen', 'hybrid:keyproj_fp32'),
+    ('parity, encoder trunk in fp32 ATen', 'hybrid:trunk_fp32'),
+    ('parity, whole key path in fp32 ATen', 'hybrid:keypath_fp32'),
 ]
 
 
+def install_hybrid(eng, kind):
+    """Swap parts of the native key path for plain fp32 ATen ops (TF32 off) to locate what the top-k read is sensitive to."""
+    import torch.nn.functional as F
+    from deva.model.engine import Engine
+    from deva.model.native_engine import _api, _to_nhwc
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = Engine(SD)
+
+    def pair_api(x):  # fp32 NCHW -> API view of NHWC fp16 hi with the lo part riding along
+        nhwc = x.permute(0, 2, 3, 1).contiguous()
+        hi = nhwc.half()
+        v = _api(hi)
+        v._b200_lo = (nhwc - hi.float()).half()
+        return v
+
+    if kind in ('trunk_fp32', 'keypath_fp32'):
+        def encode_image(image):
+            (f16, f8, f4), feat = ref.encode_image(image.float())
+            a16 = pair_api(f16)
+            a16._b200_relu = torch.relu(_to_nhwc(a16))
+            a16._b200_relu_lo = None
+            kf = pair_api(feat)
+            kf._fp32 = feat
+            return (a16, pair_api(f8), pair_api(f4)), kf
+        eng.encode_image = encode_image
+    if kind in ('keyproj_fp32', 'keypath_fp32'):
+        def transform_key(feat, need_sk=True, need_ek=True):
+            x = getattr(feat, '_fp32', None)
+            if x is None:
+                hi = _to_nhwc(feat)
+                x = (hi.float() + feat._b200_lo.float()).permute(0, 3, 1, 2).contiguous()
+            return ref.transform_key(x, need_sk, need_ek)
+        eng.transform_key = transform_key
+
+
 def run(tag, plan):
+    hybrid = None
+    if plan and plan.startswith('hybrid:'):
+        hybrid, plan = plan.split(':', 1)[1], ''
     os.environ.pop('DEVA_B200_PLAN', None)
     os.environ['DEVA_B200_PRECISION'] = 'fast' if plan is None else 'parity'
     if plan:
@@ -43,6 +84,8 @@ def run(tag, plan):
     net = net.cuda().eval()
     net.load_weights(SD)
     core = DEVAInferenceCore(net, META['config'])
+    if hybrid:
+        install_hybrid(net.engine, hybrid)
     T = G['frames'].shape[0]
     worst, sq, n, per = 0.0, 0.0, 0, []
     for t in range(T):

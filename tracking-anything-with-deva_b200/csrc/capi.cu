@@ -168,7 +168,7 @@ DEVA_B200_API int deva_b200_conv2d(const deva_b200_conv_desc* c, deva_stream_t s
   d.out_raw = c->out_raw; d.out_relu = c->out_relu; d.out_f32 = c->out_f32;
   d.out_raw_lo = c->out_raw_lo; d.out_relu_lo = c->out_relu_lo;
   d.head_w = c->head_w; d.head_out = c->head_out; d.head_n = c->head_n;
-  d.gate_h = c->gate_h; d.gate_out = c->gate_out;
+  d.gate_h = c->gate_h; d.gate_out = c->gate_out; d.ksplit = c->ksplit;
   return launch_conv(d, S(stream));
 }
 DEVA_B200_API int deva_b200_stem_im2col(const float* src, void* dst, void* dst_lo, int b, int c, int h, int w, int k_pad,
@@ -218,9 +218,14 @@ DEVA_B200_API int deva_b200_gru(const void* values, const void* h, void* out, in
                                 deva_stream_t stream) {
   return ew_gru(H(values), H(h), H(out), pixels, c, S(stream));
 }
-DEVA_B200_API int deva_b200_key_tail(const float* y, int ld, int q, int ck, float* key, float* shrinkage,
-                                     float* selection, deva_stream_t stream) {
-  return ew_key_tail(y, ld, q, ck, key, shrinkage, selection, S(stream));
+DEVA_B200_API int deva_b200_sum_parts(const float* parts, int n_parts, int64_t part_stride, const void* res,
+                                      const void* res_lo, void* raw, void* raw_lo, void* relu, void* relu_lo, int64_t n,
+                                      deva_stream_t stream) {
+  return ew_sum_parts(parts, n_parts, part_stride, H(res), H(res_lo), H(raw), H(raw_lo), H(relu), H(relu_lo), n, S(stream));
+}
+DEVA_B200_API int deva_b200_key_tail(const float* y, int ld, int q, int ck, int n_parts, int64_t part_stride, float* key,
+                                     float* shrinkage, float* selection, deva_stream_t stream) {
+  return ew_key_tail(y, ld, q, ck, n_parts, part_stride, key, shrinkage, selection, S(stream));
 }
 DEVA_B200_API int deva_b200_output_tail(const float* logits, float* agg, float* prob, float* logits_out, int k, int h,
                                         int w, deva_stream_t stream) {

@@ -71,6 +71,12 @@ struct Params {
   const __half* gate_h;  // EPI_GATES: previous hidden state [batch, ho, wo, gate_c]
   __half* gate_out;
   int gate_c;
+  // split-K (fp32 output only): unit = (k-split, tile); split ks accumulates k-iterations [ks*k_per_split, ...) in its own
+  // TMEM accumulator and writes its partial sum to out_f32 + ks*f32_split_stride (bias in split 0).  The consumer adds
+  // the partials in fp32 on the CUDA cores: the tensor core's accumulator rounds toward zero at every step, which
+  // costs a split-precision conv with a deep K loop ~1e-5 relative (tools/accum_probe.py); short chains do not.
+  int ksplit, k_per_split;
+  long long f32_split_stride;
 };
 
 struct Maps {
@@ -121,7 +127,9 @@ __device__ __forceinline__ void store_split(const float (&v)[32], __half* hi, __
 // Work unit `u` of a cluster -> this CTA's tile.  Units enumerate (channel tile, group of cs pixel tiles); CTA `rank`
 // of the cluster takes pixel tile mg*cs + rank.  A pixel tile index past the end ("phantom") is clamped so the CTA
 // still takes part in the shared weight pipeline, and flagged so its epilogue stores nothing.
-__device__ __forceinline__ bool tile_decode(int u, int rank, const Params& p, int& b, int& y0, int& x0, int& n0) {
+__device__ __forceinline__ bool tile_decode(int u, int rank, const Params& p, int& b, int& y0, int& x0, int& n0, int& ks) {
+  ks = u % p.ksplit;
+  u /= p.ksplit;
   const int nidx = u % p.n_tiles;
   int m = (u / p.n_tiles) * p.cs + rank;
   const bool real = m < p.m_tiles;
@@ -173,7 +181,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
   const int cs = p.cs;
   const int rank = (cs > 1) ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
-  const int total_units = ((p.m_tiles + cs - 1) / cs) * p.n_tiles;
+  const int total_units = ((p.m_tiles + cs - 1) / cs) * p.n_tiles * p.ksplit;
   const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
   const int k_iters = p.taps * p.cblocks;
   // PAIR: both CTAs' loads are credited to the leader's barrier -> it expects the bytes of both
@@ -205,12 +213,13 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       uint32_t phase = 0;
       const int slice_rows = p.nt / cs;
       for (int u = cluster_id; u < total_units; u += n_clusters) {
-        int b, y0, x0, n0;
-        tile_decode(u, rank, p, b, y0, x0, n0);
-        for (int t = 0; t < p.taps; ++t) {
+        int b, y0, x0, n0, ks;
+        tile_decode(u, rank, p, b, y0, x0, n0, ks);
+        const int k_lo = ks * p.k_per_split, k_hi = min(k_iters, k_lo + p.k_per_split);
+        for (int t = k_lo / p.cblocks; t < p.taps && t * p.cblocks < k_hi; ++t) {
           int c[5] = {0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b, 0};  // (channel, x, y, image, 1)
           const CUtensorMap* am = &maps.act[p.tap_map[t]];
-          for (int cb = 0; cb < p.cblocks; ++cb) {
+          for (int cb = max(0, k_lo - t * p.cblocks); cb < p.cblocks && t * p.cblocks + cb < k_hi; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
             c[0] = cb * BK;
             if constexpr (PAIR) {
@@ -245,7 +254,8 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
         mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int ki = 0; ki < k_iters; ++ki) {
+        const int my_k = min(k_iters, (u % p.ksplit + 1) * p.k_per_split) - (u % p.ksplit) * p.k_per_split;
+        for (int ki = 0; ki < my_k; ++ki) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
@@ -282,8 +292,8 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
     }
     int it = 0;
     for (int u = cluster_id; u < total_units; u += n_clusters, ++it) {
-      int b, y0, x0, n0;
-      const bool real = tile_decode(u, rank, p, b, y0, x0, n0);
+      int b, y0, x0, n0, ks;
+      const bool real = tile_decode(u, rank, p, b, y0, x0, n0, ks);
       const int y = y0 + ty, x = x0 + tx;
       const bool live = real && (y < p.ho) && (x < p.wo);
       const long long pix = ((long long)b * p.ho + y) * p.wo + x;
@@ -377,10 +387,12 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
         const int ch0 = n0 + c * 32;
         if (live && ch0 < p.cout) {
           if (ch0 + 32 <= p.cout && vec_ok) {
+            if (ks == 0) {  // partial sums of the later k-splits carry no bias
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(p.bias + ch0 + j);
-              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(p.bias + ch0 + j);
+                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+              }
             }
             if (p.rank1_w) {
 #pragma unroll
@@ -438,16 +450,16 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
               }
             }
             if (p.out_f32) {
+              float* o32 = p.out_f32 + ks * p.f32_split_stride + off + c * 32;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(p.out_f32 + off + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           } else {  // ragged channel tail (e.g. Cout = 1, 129): scalar path
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int ch = ch0 + j;
               if (ch < p.cout) {
-                float o = v[j] + p.bias[ch];
+                float o = v[j] + (ks == 0 ? p.bias[ch] : 0.f);
                 if (p.rank1_w) o = fmaf(p.rank1_w[ch], r1x, o);
                 if (res) o += __half2float(res[c * 32 + j]);
                 if (res_lo) o += __half2float(res_lo[c * 32 + j]);
@@ -462,7 +474,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
                   p.out_relu[off + c * 32 + j] = hv;
                   if (p.out_relu_lo) p.out_relu_lo[off + c * 32 + j] = __float2half_rn(ro - __half2float(hv));
                 }
-                if (p.out_f32) p.out_f32[off + c * 32 + j] = o;
+                if (p.out_f32) p.out_f32[ks * p.f32_split_stride + off + c * 32 + j] = o;
               }
             }
           }
@@ -637,7 +649,21 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
     return 3;
   }
   if (cs == 1) maps.wgt_slice = maps.wgt;
-  const long long units = (long long)((p.m_tiles + cs - 1) / cs) * p.n_tiles;
+  // split-K: fp32 output only, one CTA per unit (no clusters)
+  p.ksplit = d.ksplit > 1 ? d.ksplit : 1;
+  const int k_iters_total = p.taps * p.cblocks;
+  if (p.ksplit > 1) {
+    B200_REQUIRE(d.out_f32 && !d.out_raw && !d.out_relu && !d.res && !d.rank1_w && !d.head_w && !d.gate_out,
+                 "conv: split-K writes fp32 partial sums only (no residual / rank-1 / head / gates / fp16 outputs)");
+    B200_REQUIRE(p.ksplit <= k_iters_total, "conv: ksplit %d exceeds the %d k-iterations", p.ksplit, k_iters_total);
+    cs = 1;
+    p.cs = 1;
+    maps.wgt_slice = maps.wgt;
+  }
+  p.k_per_split = (k_iters_total + p.ksplit - 1) / p.ksplit;
+  p.ksplit = (k_iters_total + p.k_per_split - 1) / p.k_per_split;  // no empty trailing split
+  p.f32_split_stride = (long long)d.batch * ho * wo * d.cout;
+  const long long units = (long long)((p.m_tiles + cs - 1) / cs) * p.n_tiles * p.ksplit;
   // co-resident clusters (a GPC with a leftover odd SM count strands SMs for cs = 4): ask the runtime once
   static int max_clusters_dev[kMaxDevices][5] = {{0}};
   int* max_clusters = max_clusters_dev[device_slot()];

@@ -38,6 +38,7 @@ struct ConvDesc {
   // optional fused gate epilogue (see include/deva_b200.h): h' = f*h*(1-u) + u*tanh(n) on the fp32 accumulators
   const void* gate_h;
   void* gate_out;
+  int ksplit;            // > 1: split the K loop; out_f32 is [ksplit_effective, batch, ho, wo, cout] partial sums
 };
 
 int launch_conv(const ConvDesc& d, cudaStream_t stream);

@@ -465,16 +465,65 @@ gru_kernel(const __half* __restrict__ values, const __half* __restrict__ h, __ha
 
 // ---------------------------------------------------------------- key projection tail (modules.py:73-78)
 // y fp32 [Q, ld] = [key(CK) | d(1) | e(CK)] -> key [Q,CK], shrinkage [Q] = d^2+1, selection [Q,CK] = sigmoid(e)
-__global__ void key_tail_kernel(const float* __restrict__ y, int ld, int Q, int CK, float* __restrict__ key,
-                                float* __restrict__ shr, float* __restrict__ sel) {
+__global__ void key_tail_kernel(const float* __restrict__ y, int ld, int Q, int CK, int n_parts, long long part_stride,
+                                float* __restrict__ key, float* __restrict__ shr, float* __restrict__ sel) {
+  // y = n_parts fp32 partial sums (split-K of the key projection conv), added here in a fixed order with RN adds
   const long long total = (long long)Q * CK;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const long long q = i / CK;
     const int c = (int)(i - q * CK);
     const float* row = y + q * ld;
-    key[i] = row[c];
-    sel[i] = sigmoidf_(row[CK + 1 + c]);
-    if (c == 0) shr[q] = row[CK] * row[CK] + 1.f;
+    float k = row[c], e = row[CK + 1 + c], d = (c == 0) ? row[CK] : 0.f;
+    for (int p = 1; p < n_parts; ++p) {
+      const float* rp = row + p * part_stride;
+      k += rp[c];
+      e += rp[CK + 1 + c];
+      if (c == 0) d += rp[CK];
+    }
+    key[i] = k;
+    sel[i] = sigmoidf_(e);
+    if (c == 0) shr[q] = d * d + 1.f;
+  }
+}
+
+// ---------------------------------------------------------------- split-K finish
+// out = sum_p parts[p] (+ res + res_lo), written as fp16 (hi, lo) pairs raw and / or ReLU'd: completes a split-precision
+// convolution whose K loop ran as several short accumulation chains (conv.cu, `ksplit`).  The partial sums are added
+// with round-to-nearest fp32 adds in a fixed order; part 0 carries the bias.
+__global__ void __launch_bounds__(256)
+sum_parts_kernel(const float* __restrict__ parts, int n_parts, long long part_stride, const __half* __restrict__ res,
+                 const __half* __restrict__ res_lo, __half* __restrict__ raw, __half* __restrict__ raw_lo,
+                 __half* __restrict__ relu, __half* __restrict__ relu_lo, long long n8) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+    const long long off = i * 8;
+    float v[8], t[8];
+    const float4 a = *reinterpret_cast<const float4*>(parts + off), b = *reinterpret_cast<const float4*>(parts + off + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    for (int p = 1; p < n_parts; ++p) {
+      const float* src = parts + p * part_stride + off;
+      const float4 c = *reinterpret_cast<const float4*>(src), d = *reinterpret_cast<const float4*>(src + 4);
+      v[0] += c.x; v[1] += c.y; v[2] += c.z; v[3] += c.w; v[4] += d.x; v[5] += d.y; v[6] += d.z; v[7] += d.w;
+    }
+    if (res) {
+      ld8(res + off, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += t[e];
+    }
+    if (res_lo) {
+      ld8(res_lo + off, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += t[e];
+    }
+    if (raw) {
+      if (raw_lo) st8_split(raw + off, raw_lo + off, v);
+      else st8(raw + off, v, false);
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+      if (relu_lo) st8_split(relu + off, relu_lo + off, v);
+      else st8(relu + off, v, false);
+    }
   }
 }
 
@@ -668,8 +717,18 @@ int ew_gru(const __half* values, const __half* h, __half* out, long long pixels,
   B200_LAUNCH_CHECK();
   return 0;
 }
-int ew_key_tail(const float* y, int ld, int Q, int CK, float* key, float* shr, float* sel, cudaStream_t s) {
-  ew::key_tail_kernel<<<grid_of((long long)Q * CK), 256, 0, s>>>(y, ld, Q, CK, key, shr, sel);
+int ew_key_tail(const float* y, int ld, int Q, int CK, int n_parts, long long part_stride, float* key, float* shr,
+                float* sel, cudaStream_t s) {
+  B200_REQUIRE(n_parts >= 1, "key_tail: n_parts %d", n_parts);
+  ew::key_tail_kernel<<<grid_of((long long)Q * CK), 256, 0, s>>>(y, ld, Q, CK, n_parts, part_stride, key, shr, sel);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+int ew_sum_parts(const float* parts, int n_parts, long long part_stride, const __half* res, const __half* res_lo,
+                 __half* raw, __half* raw_lo, __half* relu, __half* relu_lo, long long n, cudaStream_t s) {
+  B200_REQUIRE(n_parts >= 1 && n % 8 == 0 && part_stride % 4 == 0 && (raw || relu), "sum_parts: bad shape");
+  ew::sum_parts_kernel<<<grid_of(n / 8), 256, 0, s>>>(parts, n_parts, part_stride, res, res_lo, raw, raw_lo, relu, relu_lo,
+                                                       n / 8);
   B200_LAUNCH_CHECK();
   return 0;
 }

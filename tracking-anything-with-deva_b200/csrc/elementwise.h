@@ -19,7 +19,10 @@ int ew_cbam(const __half* x, const float* w1, const float* b1, const float* w2, 
             const float* bs, float* scratch, __half* raw, __half* relu, int B, int H, int W, int C, int R,
             cudaStream_t s);
 int ew_gru(const __half* values, const __half* h, __half* out, long long pixels, int C, cudaStream_t s);
-int ew_key_tail(const float* y, int ld, int Q, int CK, float* key, float* shr, float* sel, cudaStream_t s);
+int ew_sum_parts(const float* parts, int n_parts, long long part_stride, const __half* res, const __half* res_lo,
+                 __half* raw, __half* raw_lo, __half* relu, __half* relu_lo, long long n, cudaStream_t s);
+int ew_key_tail(const float* y, int ld, int Q, int CK, int n_parts, long long part_stride, float* key, float* shr,
+                float* sel, cudaStream_t s);
 int ew_output_tail(const float* logits, float* agg, float* prob, float* logits_out, int K, int h, int w, cudaStream_t s);
 int ew_head_gather3x3(const float* z, float* out, float bias, int B, int H, int W, cudaStream_t s);
 int ew_transpose_append(const __half* src, __half* dst, long long ld_dst, int n, int C, cudaStream_t s);

@@ -29,7 +29,7 @@ class ConvDesc(ctypes.Structure):
                 ('out_raw', c_void_p), ('out_relu', c_void_p), ('out_f32', c_void_p),
                 ('out_raw_lo', c_void_p), ('out_relu_lo', c_void_p),
                 ('head_w', c_void_p), ('head_out', c_void_p), ('head_n', c_int32),
-                ('gate_h', c_void_p), ('gate_out', c_void_p)]
+                ('gate_h', c_void_p), ('gate_out', c_void_p), ('ksplit', c_int32)]
 
 
 _SIGNATURES = {
@@ -85,7 +85,9 @@ _SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
     'deva_b200_gru': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
-    'deva_b200_key_tail': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'deva_b200_sum_parts': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int64, c_void_p]),
+    'deva_b200_key_tail': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     'deva_b200_output_tail': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'deva_b200_head_gather3x3': (c_int, [c_void_p, c_void_p, ctypes.c_float, c_int, c_int, c_int, c_void_p]),
     'deva_b200_transpose_append': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
@@ -273,10 +275,10 @@ def _p(t):
 def conv2d(x, batch, h, w, cin_pad, w_packed, kh, stride, cout, cout_pad, nt, th, tw, bias, x2=None, x_lo=None, res=None,
            res_lo=None, res_broadcast=False, rank1_w=None, rank1_x=None, out_raw=None, out_relu=None, out_f32=None,
            out_raw_lo=None, out_relu_lo=None, head_w=None, head_out=None, head_n=0, gate_h=None, gate_out=None,
-           split_mode=0):
+           split_mode=0, ksplit=0):
     d = ConvDesc(_p(x), _p(x2), _p(x_lo), split_mode, batch, h, w, cin_pad, _p(w_packed), kh, kh, stride, cout, cout_pad, nt, th, tw,
                  _p(bias), _p(res), _p(res_lo), int(res_broadcast), _p(rank1_w), _p(rank1_x), _p(out_raw), _p(out_relu),
-                 _p(out_f32), _p(out_raw_lo), _p(out_relu_lo), _p(head_w), _p(head_out), head_n, _p(gate_h), _p(gate_out))
+                 _p(out_f32), _p(out_raw_lo), _p(out_relu_lo), _p(head_w), _p(head_out), head_n, _p(gate_h), _p(gate_out), ksplit)
     _check(lib().deva_b200_conv2d(ctypes.byref(d), _stream()), 'conv2d')
 
 
@@ -329,9 +331,14 @@ def gru(values, h, out, pixels, c):
     _check(lib().deva_b200_gru(_ptr(values), _ptr(h), _ptr(out), pixels, c, _stream()), 'gru')
 
 
-def key_tail(y, ld, q, ck, key, shrinkage, selection):
-    _check(lib().deva_b200_key_tail(_ptr(y), ld, q, ck, _ptr(key), _ptr(shrinkage), _ptr(selection), _stream()),
-           'key_tail')
+def sum_parts(parts, n_parts, part_stride, n, res=None, res_lo=None, raw=None, raw_lo=None, relu=None, relu_lo=None):
+    _check(lib().deva_b200_sum_parts(_ptr(parts), n_parts, part_stride, _ptr(res), _ptr(res_lo), _ptr(raw), _ptr(raw_lo),
+                                     _ptr(relu), _ptr(relu_lo), n, _stream()), 'sum_parts')
+
+
+def key_tail(y, ld, q, ck, key, shrinkage, selection, n_parts=1, part_stride=0):
+    _check(lib().deva_b200_key_tail(_ptr(y), ld, q, ck, n_parts, part_stride, _ptr(key), _ptr(shrinkage), _ptr(selection),
+                                    _stream()), 'key_tail')
 
 
 def output_tail(logits, agg, prob, logits_out, k, h, w):

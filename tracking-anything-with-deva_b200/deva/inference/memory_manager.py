@@ -229,14 +229,24 @@ class MemoryManager:
             self._banks[b].append_work(key, shr, sel, vals)
 
         if self.use_long_term:
-            for b in list(self._banks.keys()):
-                bank = self._banks[b]
-                if bank.work_size >= self.max_work_tokens:
-                    if bank.long_size >= (self.max_long_tokens - self.num_prototypes):
-                        if not self.count_long_term_usage:
-                            raise RuntimeError('I did not count usage!')  # kv_memory_store.py:189-190
-                        bank.evict_long(self.max_long_tokens - self.num_prototypes)
-                    self.compress_features(b)
+            self._maintain_long_term()
+
+    def _maintain_long_term(self) -> None:
+        """Long-term clean-up after an append (memory_manager.py:207-218)."""
+        for b in list(self._banks.keys()):
+            bank = self._banks[b]
+            if bank.work_size >= self.max_work_tokens:
+                if self._long_size(bank) >= (self.max_long_tokens - self.num_prototypes):
+                    if not self.count_long_term_usage:
+                        raise RuntimeError('I did not count usage!')  # kv_memory_store.py:189-190
+                    self._evict_long(bank, self.max_long_tokens - self.num_prototypes)
+                self.compress_features(b)
+
+    def _long_size(self, bank: BucketBank) -> int:
+        return bank.long_size
+
+    def _evict_long(self, bank: BucketBank, max_size: int) -> None:
+        bank.evict_long(max_size)
 
     def compress_features(self, bucket_id: int) -> None:
         """Consolidate the middle of the working memory into prototypes (memory_manager.py:231-249)."""

@@ -86,11 +86,13 @@ class LayerTable:
                 L[q + '.c2'] = _fold(sd, q + '.conv2', q + '.bn2', 1, 1)
                 if (q + '.downsample.0.weight') in sd:
                     L[q + '.ds'] = _fold(sd, q + '.downsample.0', q + '.downsample.1', s, 0)
-        self._fusion(L, sd, p + '.fuser', 512)
+        # the fusers see cat[f16 (pix_feat_dim channels, shared), per-object feature]: split at the checkpoint's own width
+        pix_dim = sd['pixel_encoder.proj1.weight'].shape[0]
+        self._fusion(L, sd, p + '.fuser', pix_dim)
         L[p + '.gru'] = _fold(sd, p + '.sensory_update.transform', None, 1, 1)
         # ---- mask decoder (big_modules.py:130-212)
         p = 'mask_decoder'
-        self._fusion(L, sd, p + '.fuser', 512)
+        self._fusion(L, sd, p + '.fuser', pix_dim)
         sc = _fold(sd, p + '.sensory_compress', None, 1, 0)
         L[p + '.sensory_compress'] = sc
         L[p + '.skip8'] = _fold(sd, p + '.decoder_feat_proc.transforms.0', None, 1, 0)

@@ -52,6 +52,7 @@ class NativeEngine:
         if self.precision not in ('parity', 'fast'):
             raise RuntimeError(f"deva_b200: DEVA_B200_PRECISION must be 'parity' or 'fast', got {self.precision!r}")
         self.parity = self.precision == 'parity'
+        self.key_ksplit = int(os.environ.get('DEVA_B200_KEY_KSPLIT', '8'))
         self.plan_override = [tuple(item.split('=')) for item in os.environ.get('DEVA_B200_PLAN', '').split(',') if '=' in item]
         for _, mode in self.plan_override:
             if mode not in ('precise', 'act_lo', 'w_lo', 'single') or not self.parity:
@@ -144,12 +145,15 @@ class NativeEngine:
             lo = torch.zeros_like(x)
         _, h, w, _ = x.shape
         pc = self.P['key_proj.all']
-        y = ops.conv_ex(x, pc, x_lo=lo, want_f32=True).f32  # [1,h,w,2*CK+1] fp32
+        # split-K: the projection's 3 x 9 x Cin/64 k-iterations run as KSPLIT short accumulation chains whose fp32 partial
+        # sums key_tail adds on the CUDA cores.  One TMEM accumulator over the whole loop (round-toward-zero at every
+        # step) left the keys 7.5e-5 off - enough to flip near-tied top-k members (profiles/r02_keypath_accumulation.md).
+        y = ops.conv_ex(x, pc, x_lo=lo, want_f32=True, ksplit=self.key_ksplit).f32  # [parts,1,h,w,2*CK+1] fp32
         q, ck = h * w, self.key_dim
         key = torch.empty(q, ck, dtype=torch.float32, device=x.device)
         sel = torch.empty(q, ck, dtype=torch.float32, device=x.device)
         shr = torch.empty(q, dtype=torch.float32, device=x.device)
-        nat.key_tail(y, pc.cout, q, ck, key, shr, sel)
+        nat.key_tail(y, pc.cout, q, ck, key, shr, sel, n_parts=y.shape[0], part_stride=y[0].numel())
         return (key.view(1, h, w, ck).permute(0, 3, 1, 2), shr.view(1, 1, h, w) if need_sk else None,
                 sel.view(1, h, w, ck).permute(0, 3, 1, 2) if need_ek else None)
 

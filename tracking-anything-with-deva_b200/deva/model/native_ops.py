@@ -9,6 +9,8 @@ import torch
 
 from deva import _native as nat
 
+MAX_CHAIN = 32  # longest single accumulation chain of a split-precision conv (k-iterations of 64 channels)
+CHAIN = 27      # chain length when a longer loop is split (= one 3x3 filter over 64 channels in three passes)
 PROFILE = None  # set to a list by bench.py to collect (start event, end event, algorithmic FLOPs, MMA passes) per conv
 
 _TILES = ((1, 128), (2, 64), (4, 32), (8, 16), (16, 8), (32, 4))
@@ -119,7 +121,7 @@ def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = Non
             res: Optional[torch.Tensor] = None, res_lo: Optional[torch.Tensor] = None,
             rank1_x: Optional[torch.Tensor] = None, want_raw: bool = False, want_relu: bool = False,
             want_f32: bool = False, want_lo: bool = False, head_w: Optional[torch.Tensor] = None,
-            gate_h: Optional[torch.Tensor] = None) -> ConvOut:
+            gate_h: Optional[torch.Tensor] = None, ksplit: int = 0) -> ConvOut:
     """x fp16 NHWC [B,H,W,cin_pad] (+ x2: implicit channel concat, or + x_lo: split precision) -> ConvOut."""
     assert x.dtype == torch.float16 and x.is_contiguous() and x.shape[-1] == pc.cin_pad, (x.shape, pc.cin_pad)
     assert (x2 is not None) == pc.two_inputs and (x_lo is not None) == pc.takes_lo, (x_lo is None, pc.takes_lo)
@@ -134,6 +136,25 @@ def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = Non
     def new(dtype=torch.float16):
         return torch.empty(b, ho, wo, pc.cout, dtype=dtype, device=dev)
 
+    # Split-precision layers keep at most MAX_CHAIN k-iterations in one TMEM accumulator: the tensor core rounds toward
+    # zero at every accumulation step, and a deep K loop (3x3 x 256 channels x 3 passes = 108 k-iterations) leaves a
+    # systematic ~1e-5 relative error that the top-k read downstream of the key path does not tolerate
+    # (tools/accum_probe.py, profiles/r02_keypath_accumulation.md).  Longer loops run as chains of <= CHAIN k-iterations
+    # whose fp32 partial sums are added - with the bias, the residual and the output conversions - by sum_parts.
+    k_iters = pc.k * pc.k * (pc.cin_pad // 64) * (3 if pc.precise else (2 if (pc.act_lo or pc.w_lo or pc.two_inputs) else 1))
+    if (pc.precise and ksplit == 0 and k_iters > MAX_CHAIN and not (want_f32 or head_w is not None or pc.rank1_w is not None)
+            and pc.cout % 8 == 0 and (res is None or res.shape[0] == b)):
+        parts = conv_ex(x, pc, x_lo=x_lo, want_f32=True, ksplit=-(-k_iters // CHAIN)).f32
+        o = ConvOut()
+        if want_raw:
+            o.raw = torch.empty(b, ho, wo, pc.cout, dtype=torch.float16, device=dev)
+            o.raw_lo = torch.empty_like(o.raw) if want_lo else None
+        if want_relu:
+            o.relu = torch.empty(b, ho, wo, pc.cout, dtype=torch.float16, device=dev)
+            o.relu_lo = torch.empty_like(o.relu) if want_lo else None
+        nat.sum_parts(parts, parts.shape[0], parts[0].numel(), parts[0].numel(), res=res, res_lo=res_lo, raw=o.raw,
+                      raw_lo=o.raw_lo, relu=o.relu, relu_lo=o.relu_lo)
+        return o
     o = ConvOut()
     if want_raw:
         o.raw = new()
@@ -143,6 +164,10 @@ def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = Non
         o.relu_lo = new() if want_lo else None
     if want_f32:
         o.f32 = new(torch.float32)
+        if ksplit > 1:  # fp32 partial sums [parts, b, ho, wo, cout] of a split K loop; the consumer adds them
+            k_iters = pc.k * pc.k * (pc.cin_pad // 64) * (3 if pc.precise else (2 if (pc.act_lo or pc.w_lo or pc.two_inputs) else 1))
+            per = -(-k_iters // ksplit)
+            o.f32 = torch.empty(-(-k_iters // per), b, ho, wo, pc.cout, dtype=torch.float32, device=dev)
     res_b = False
     if res is not None:
         assert res.dtype == torch.float16 and res.is_contiguous() and res.shape[1:] == (ho, wo, pc.cout)
@@ -168,7 +193,7 @@ def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = Non
                x2=x2, x_lo=x_lo, res=res, res_lo=res_lo, res_broadcast=res_b, rank1_w=pc.rank1_w,
                rank1_x=rank1_x if pc.rank1_w is not None else None, out_raw=o.raw, out_relu=o.relu, out_f32=o.f32,
                out_raw_lo=o.raw_lo, out_relu_lo=o.relu_lo, head_w=head_w, head_out=o.head, head_n=head_n,
-               gate_h=gate_h, gate_out=o.hidden, split_mode=pc.split_mode)
+               gate_h=gate_h, gate_out=o.hidden, split_mode=pc.split_mode, ksplit=ksplit)
     if PROFILE is not None:
         ev1.record()
         flops = 2.0 * b * ho * wo * pc.cout * pc.k * pc.k * pc.cin * (2 if pc.two_inputs else 1)

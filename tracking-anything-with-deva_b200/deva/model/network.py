@@ -109,12 +109,15 @@ class DEVA(nn.Module):
         if selector is not None:
             prob = prob * selector
         if independent_objects:
+            # per-object softmax against its own background (network.py:148-162); like the reference, the second
+            # return value is the up-sampled aggregated LOGITS [K,2,H,W], not their softmax
             k, h, w = prob.shape[1:]
-            each = self.aggregate(prob.view(k, 1, h, w), dim=1)
-            each = F.softmax(F.interpolate(each, scale_factor=4, mode='bilinear', align_corners=False), dim=1)
+            each_logits = self.aggregate(prob.view(k, 1, h, w), dim=1)
+            each_logits = F.interpolate(each_logits, scale_factor=4, mode='bilinear', align_corners=False)
+            each = F.softmax(each_logits, dim=1)
             background = each[:, 0].min(dim=0)[0]
             prob = torch.cat([background.unsqueeze(0), each[:, 1]], dim=0).unsqueeze(0)
-            return sensory, each, prob
+            return sensory, each_logits, prob
         logits = self.aggregate(prob, dim=1)
         logits = F.interpolate(logits, scale_factor=4, mode='bilinear', align_corners=False)
         return sensory, logits, F.softmax(logits, dim=1)
