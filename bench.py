@@ -44,6 +44,14 @@ WORKLOADS = {
     'c3': dict(name='c3: 1080p, 16 objects, 10k memory slots, full encode->read->decode', h=1080, w=1920, k=16,
                n=10000),
     'c2': dict(name='c2: 480p, 5 objects, 2k memory slots', h=480, w=854, k=5, n=2000),
+    # BASELINE configs[3]: 64 independent 480p clips sharded round-robin over the ranks (clip-parallel; a step = one frame
+    # of EVERY clip, total work fixed -> strong scaling)
+    'c4': dict(name='c4: 64 independent 480p clips, 5 objects, 2k memory slots each, clip-parallel', h=480, w=854, k=5,
+               n=2000, clips=64),
+    # BASELINE configs[4]: ONE 1080p video, 32 objects, 50k memory slots: bank sharded over the ranks + object-parallel
+    # decode (deva.inference.sharded_core); every rank sees every frame, total work fixed -> strong scaling
+    'c5': dict(name='c5: single 1080p clip, 32 objects, 50k memory slots, bank-sharded + object-parallel', h=1080, w=1920,
+               k=32, n=50000, sharded=True),
 }
 METRIC = 'propagation FPS @1080p, 10k-mem, 16 obj; affinity GEMM TFLOPS vs bf16 peak'
 
@@ -122,37 +130,56 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ ours
+def make_network(device):
+    from deva.model.network import DEVA
+    from deva.model.param_spec import synthetic_state_dict
+    net = DEVA(base_config()).to(device).eval()
+    net.load_weights({k: v.to(device) for k, v in synthetic_state_dict(seed=0).items()})
+    return net
+
+
 class Clip:
-    """One clip on one GPU: network, core, bank pre-filled to wl['n'] slots."""
-    def __init__(self, wl, device, seed):
+    """One clip on one GPU (or, for a sharded workload, this rank's share of the one clip): core + bank pre-filled to
+    wl['n'] slots."""
+    def __init__(self, wl, device, seed, net=None):
         from deva import _native as nat
         from deva.inference.inference_core import DEVAInferenceCore
-        from deva.model.network import DEVA
-        from deva.model.param_spec import synthetic_state_dict
         nat.require_device()
         self.nat, self.wl, self.device = nat, wl, device
         cfg = base_config()
-        net = DEVA(cfg).to(device).eval()
-        net.load_weights({k: v.to(device) for k, v in synthetic_state_dict(seed=0).items()})
-        self.core = DEVAInferenceCore(net, cfg)
+        net = net or make_network(device)
+        if wl.get('sharded'):
+            from deva.inference.sharded_core import ShardedDEVAInferenceCore, token_bounds
+            self.core = ShardedDEVAInferenceCore(net, cfg)
+            world, rank = self.core.world, self.core.rank
+        else:
+            self.core = DEVAInferenceCore(net, cfg)
+            world, rank = 1, 0
         self.frames_host = synth_frames(wl, 5, seed).pin_memory()
         self.frames_dev = self.frames_host.to(device)
         ids = list(range(1, wl['k'] + 1))
         self.core.step(self.frames_dev[0], synth_mask(wl).to(device), ids)  # first frame -> Q memory tokens
         mem = self.core.memory
         bank = next(iter(mem._banks.values()))
-        self.q = mem.HW
-        extra = wl['n'] - bank.work_size
+        self.q = (-(-wl['h'] // 16)) * (-(-wl['w'] // 16))
+        extra = wl['n'] - self.q
         assert extra >= 0, 'bank already larger than the configured slot count'
-        if extra > 0:  # random-init top-up to exactly n slots (BASELINE.md section 4 generator)
+        if extra > 0:  # random-init top-up to exactly n slots (BASELINE.md section 4 generator); every rank draws the
+            # same tokens and keeps its slice
+            lo, hi = (0, extra) if world == 1 else token_bounds(extra, world, rank)
             g = torch.Generator(device=device).manual_seed(seed + 1)
-            key = torch.randn(1, CK, extra, 1, device=device, generator=g)
-            shr = 1 + torch.rand(1, 1, extra, 1, device=device, generator=g)
-            sel = torch.sigmoid(torch.randn(1, CK, extra, 1, device=device, generator=g))
-            val = torch.randn(1, wl['k'], CV, extra, 1, device=device, generator=g)
-            mem.add_memory(key, shr, val, ids, selection=sel)
+            key = torch.randn(1, CK, extra, 1, device=device, generator=g)[:, :, lo:hi]
+            shr = (1 + torch.rand(1, 1, extra, 1, device=device, generator=g))[:, :, lo:hi]
+            sel = torch.sigmoid(torch.randn(1, CK, extra, 1, device=device, generator=g))[:, :, lo:hi]
+            val = torch.cat([torch.randn(1, 1, CV, extra, 1, device=device, generator=g)[:, :, :, lo:hi]
+                             for _ in range(wl['k'])], 1)
+            mem.add_memory(key.contiguous(), shr.contiguous(), val, ids, selection=sel.contiguous())
         self.bank, self.mark = bank, bank.hi
-        assert bank.work_size == wl['n']
+        total = torch.tensor([bank.work_size], device=device)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(total)
+        assert int(total) == wl['n'], (int(total), wl['n'])
         self.i = 0
 
     def clamp(self):
@@ -193,6 +220,31 @@ class Clip:
         return host
 
 
+class ClipSet:
+    """Workload c4: this rank's share (round-robin, deva.utils.dist_utils.assign_clips) of the independent clips, all
+    driven through ONE network; a step advances every clip by one frame."""
+    def __init__(self, wl, device, rank, world):
+        from deva.utils.dist_utils import assign_clips
+        net = make_network(device)
+        self.ids = assign_clips(wl['clips'], world, rank)
+        self.clips = [Clip(wl, device, seed=100 + i, net=net) for i in self.ids]
+        self.nat, self.wl, self.q = self.clips[0].nat, wl, self.clips[0].q
+        self.core = self.clips[0].core
+        self.frames_host = self.clips[0].frames_host
+
+    def step_resident(self):
+        for c in self.clips:
+            c.step_resident()
+
+    def step_e2e(self):
+        for c in self.clips:
+            c.step_e2e()
+
+    def step_e2e_fused_io(self):
+        for c in self.clips:
+            c.step_e2e_fused_io()
+
+
 def timed(fn, steps, dist_on):
     import torch.distributed as dist
     if dist_on:
@@ -226,7 +278,15 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=device)
     torch.backends.cudnn.benchmark = True
     wl = WORKLOADS[args.workload]
-    clip = Clip(wl, device, seed=100 + rank)
+    if 'clips' in wl:      # c4: fixed set of clips split over the ranks
+        clip = ClipSet(wl, device, rank, world)
+        frames_per_step, scaling, n_clips_rank = wl['clips'], 'strong', len(clip.clips)
+    elif wl.get('sharded'):  # c5: one clip, every rank works on every frame
+        clip = Clip(wl, device, seed=100)
+        frames_per_step, scaling, n_clips_rank = 1, 'strong', 1
+    else:                  # c3 / c2: one clip per rank
+        clip = Clip(wl, device, seed=100 + rank)
+        frames_per_step, scaling, n_clips_rank = world, 'weak', 1
     nat = clip.nat
     for _ in range(max(args.warmup, 3)):
         clip.step_resident()
@@ -253,11 +313,13 @@ def run_ours(args):
     from deva.model import native_ops
     precision = getattr(clip.core.network.engine, 'precision', 'n/a')
     conv_roof = None
-    if rank == 0:
-        native_ops.PROFILE = []
+    if rank == 0 or wl.get('sharded'):  # a sharded clip steps on every rank (collectives inside the step)
+        if rank == 0:
+            native_ops.PROFILE = []
         for _ in range(5):  # exactly one memory frame
             clip.step_resident()
         torch.cuda.synchronize()
+    if rank == 0:
         prof, native_ops.PROFILE = native_ops.PROFILE, None
         conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof) / 5
         conv_flops = sum(f for _, _, f, _ in prof) / 5
@@ -291,9 +353,9 @@ def run_ours(args):
         h2d = int(clip.frames_host[0].numel() * 4)
         d2h = int(wl['h'] * wl['w'])
         out = {
-            'metric': METRIC, 'value': world * args.steps / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world,
+            'metric': METRIC, 'value': frames_per_step * args.steps / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16 MMA operands / f32 accumulate '
+            'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f16 MMA operands / f32 accumulate '
             f'(tcgen05 memory read + conv stack), precision plan {precision!r}; key path split-f16x3 (~f32)', 'data': 'synthetic',
             'config': workload_config(wl, clip.q, world),
             'roofline': {'kernel': 'fused affinity path: pack_query + sim_topk(tcgen05 fp16x3) + merge + bucket + readout_sparse(tcgen05, '
@@ -303,10 +365,11 @@ def run_ours(args):
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'ms_per_launch': read_ms, 'flops_per_launch': flops},
             'roofline_conv': conv_roof,
-            'e2e': {'value': world * args.steps / (ms_e2e * 1e-3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
-                    'd2h_bytes_per_step': d2h},
-            'e2e_fused_io': {'value': world * args.steps / (ms_e2e_io * 1e-3), 'unit': 'frames/s',
-                             'h2d_bytes_per_step': int(wl['h'] * wl['w'] * 3), 'd2h_bytes_per_step': d2h,
+            'e2e': {'value': frames_per_step * args.steps / (ms_e2e * 1e-3), 'unit': 'frames/s',
+                    'h2d_bytes_per_step': h2d * n_clips_rank, 'd2h_bytes_per_step': d2h * n_clips_rank},
+            'e2e_fused_io': {'value': frames_per_step * args.steps / (ms_e2e_io * 1e-3), 'unit': 'frames/s',
+                             'h2d_bytes_per_step': int(wl['h'] * wl['w'] * 3) * n_clips_rank,
+                             'd2h_bytes_per_step': d2h * n_clips_rank,
                              'what': 'uint8 frame upload + on-device normalise; fused argmax + id remap (deva.inference.frame_io)'},
             'gpu_launches': int(launches), 'wall_ms_per_step': wall / args.steps, 'clocks': clocks,
             'precision_plan': precision,

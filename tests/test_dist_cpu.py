@@ -69,3 +69,22 @@ def test_shard_bounds_and_localise():
     # weights of all shards add back up to the global list
     tot = sum(localise(idx, w, *shard_bounds(48, 3, r))[1] for r in range(3))
     assert torch.allclose(tot, w)
+
+
+def test_sharded_core_partitions():
+    """token / object partitions of the bank-sharded core (deva.inference.sharded_core): disjoint, exhaustive, balanced."""
+    from deva.inference.sharded_core import object_bounds, token_bounds
+    for n in (30, 1620, 8160, 7):
+        for world in (1, 2, 4, 8):
+            cover = [token_bounds(n, world, r) for r in range(world)]
+            assert cover[0][0] == 0 and cover[-1][1] == n
+            assert all(cover[i][1] == cover[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in cover]
+            assert max(sizes) - min(sizes) <= 1
+    for k in (0, 1, 2, 3, 16, 32, 33):
+        for world in (1, 2, 4, 8):
+            cover = [object_bounds(k, world, r) for r in range(world)]
+            owned = [i for a, b in cover for i in range(a, b)]
+            assert owned == list(range(k))
+            per = -(-k // world) if k else 0
+            assert all(b - a <= per for a, b in cover)
