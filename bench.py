@@ -336,6 +336,8 @@ def run_ours(args):
             'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
         flops = read_flops(wl, clip.q)
         achieved = flops / (read_ms * 1e-3) / 1e12
+        if wl.get('sharded'):  # every rank multiplies 1/world of the slots: per-GPU rate against one GPU's peak
+            achieved /= world
         traffic = conv_traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')))

@@ -9,6 +9,7 @@ from deva.model import native_ops as ops  # noqa: E402
 CASES = {
     # name: (batch, h, w, cin, cout, k, mode)
     'up84_c1': (16, 272, 480, 256, 256, 3, 'relu'),
+    'up84_c1_actlo': (16, 272, 480, 256, 256, 3, 'actlo'),   # parity plan: activations as (hi, lo), two MMA passes
     'up84_c2_res': (16, 272, 480, 256, 256, 3, 'raw+res'),
     'up84_c2_head': (16, 272, 480, 256, 256, 3, 'raw+res+head'),
     'gru': (16, 68, 120, 512, 1536, 3, 'two'),
@@ -26,20 +27,20 @@ def run(name, iters=8):
     x = torch.randn(b, h, w, cin, device=dev, generator=g).half()
     wgt = torch.randn(cout, cin * (2 if mode == 'two' else 1), k, k, device=dev, generator=g) / (cin * k * k)**0.5
     bias = torch.randn(cout, device=dev, generator=g)
-    pc = ops.PackedConv(wgt, bias, 1, two_inputs=(mode == 'two'), precise=(mode == 'precise'))
+    pc = ops.PackedConv(wgt, bias, 1, two_inputs=(mode == 'two'), precise=(mode == 'precise'), act_lo=(mode == 'actlo'))
     kw = {}
     if mode == 'two':
         kw['x2'] = torch.randn_like(x)
-    if mode == 'precise':
+    if mode in ('precise', 'actlo'):
         kw['x_lo'] = (torch.randn_like(x) * 1e-3)
     if 'res' in mode:
         kw['res'] = torch.randn(b, h, w, cout, device=dev, generator=g).half()
     if 'head' in mode:
         kw['head_w'] = torch.randn(9, cout, device=dev, generator=g)
     want = dict(want_relu=True) if mode in ('relu', ) else dict(want_raw=True)
-    if mode == 'precise':
+    if mode in ('precise', 'actlo'):
         want = dict(want_relu=True, want_lo=True)
-    passes = 3 if mode == 'precise' else (2 if mode == 'two' else 1)
+    passes = 3 if mode == 'precise' else (2 if mode in ('two', 'actlo') else 1)
     flops = 2.0 * b * h * w * cout * k * k * pc.cin_pad * passes
     for _ in range(3):
         ops.conv_ex(x, pc, **kw, **want)
