@@ -194,6 +194,13 @@ typedef struct deva_b200_conv_desc {
    * gate_out = sigmoid(f) * gate_h * (1 - sigmoid(u)) + sigmoid(u) * tanh(n), evaluated on the fp32 accumulators. */
   const void* gate_h;   /* fp16 NHWC [batch, ho, wo, cout/3] previous hidden state */
   void* gate_out;       /* fp16 NHWC [batch, ho, wo, cout/3] new hidden state */
+  /* split_mode 3: the low-order activation pass on the fp8 tensor-core path (half the cost of split_mode 1):
+   * D = (X . W16 + Xlo8 . W8) * acc_scale, W16 = fp16(W * 2^S) in w_packed, W8 = e4m3(W * 2^(S-12)) in w8_packed,
+   * Xlo8 = e4m3((x - fp16(x)) * 4096) in x_lo8, acc_scale = 2^-S.  Stride 1, cin_pad % 128 == 0. */
+  const void* x_lo8;    /* u8 NHWC [batch, h, w, cin_pad] */
+  const void* w8_packed; /* u8 [cout_pad, kh*kw*cin_pad] */
+  float acc_scale;      /* 0 = 1 */
+  void* out_relu_lo8;   /* optional u8 NHWC: e4m3 low-order part (x 4096) of the ReLU'd output */
   int32_t ksplit;       /* > 1: split the K loop into that many chains (fp32 output only): out_f32 then holds
                          * ceil(k_iters / ceil(k_iters / ksplit)) partial sums [part, batch, ho, wo, cout] (bias in part 0)
                          * for the consumer to add in fp32.  The tensor core's accumulator rounds toward zero at every
@@ -228,8 +235,10 @@ DEVA_B200_API int deva_b200_cbam(const void* x, const float* w1, const float* b1
  * wanted), the ReLU'd copy (an MMA operand) as hi, plus its remainder relu_lo when the consumer runs a second
  * activation pass (conv split_mode 1). */
 DEVA_B200_API int deva_b200_up2_add_split(const void* g, const void* g_lo, const void* skip, const void* skip_lo,
-                                          void* raw, void* raw_lo, void* relu, void* relu_lo, int b, int h, int w, int c,
-                                          deva_stream_t stream);
+                                          void* raw, void* raw_lo, void* relu, void* relu_lo, void* relu_lo8, int b, int h,
+                                          int w, int c, deva_stream_t stream);
+/* relu_lo8 (instead of relu_lo): u8 NHWC, e4m3 of (relu - fp16(relu)) * 4096 - the low-order operand of a conv with
+ * split_mode 3. */
 DEVA_B200_API int deva_b200_cbam_split(const void* x, const void* x_lo, const float* w1, const float* b1, const float* w2,
                                        const float* b2, const float* ws, const float* bs, float* scratch, void* raw,
                                        void* raw_lo, void* relu, void* relu_lo, int b, int h, int w, int c, int r,

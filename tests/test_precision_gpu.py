@@ -148,3 +148,68 @@ def test_conv_split_k_partial_sums(ksplit):
     err = float((got - ref).abs().max()) / scale
     print(f'split-K {ksplit}: max rel err {err:.2e}')
     assert err < (5e-5 if ksplit == 1 else 5e-6), err  # one chain: the accumulator's round-toward-zero shows
+
+
+def _e4m3_bytes(x):
+    return x.to(torch.float8_e4m3fn).view(torch.uint8)
+
+
+def _from_e4m3(b):
+    return b.view(torch.float8_e4m3fn).float()
+
+
+@pytest.mark.parametrize('b,h,w,cin,cout,k', [(2, 14, 18, 128, 256, 3), (5, 72, 121, 256, 256, 3), (3, 20, 33, 256, 128, 1)])
+def test_conv_fp8_correction_mode(b, h, w, cin, cout, k):
+    """split_mode 3: D = (Xh.W16 + Xlo8.W8) * 2^-S on mixed kind::f16 / kind::f8f6f4 MMAs into one accumulator.  Checked
+    (a) against the same quantised operands in fp64 (the kernel adds nothing to their error) and (b) against the exact
+    activations: the e4m3 correction pass must remove most of the single-pass operand rounding."""
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(7 + cin + k)
+    x = torch.randn(b, cin, h, w, device='cuda', generator=g).relu() * 2
+    wgt = (torch.randn(cout, cin, k, k, device='cuda', generator=g) / (cin * k * k)**0.5).half().float()
+    bias = torch.randn(cout, device='cuda', generator=g)
+    pc = ops.PackedConv(wgt, bias, 1, act_lo8=True)
+    xn = _nhwc(x)
+    xh = xn.half()
+    lo8 = _e4m3_bytes((xn - xh.float()) * 4096.0).contiguous()
+    w16 = pc.w_packed.float().view(pc.cout_pad, k, k, pc.cin_pad)[:cout, :, :, :cin].permute(0, 3, 1, 2).double()
+    w8 = _from_e4m3(pc.w8_packed).view(pc.cout_pad, k, k, pc.cin_pad)[:cout, :, :, :cin].permute(0, 3, 1, 2).double()
+    quant = (F.conv2d(xh.double().permute(0, 3, 1, 2), w16, padding=k // 2) +
+             F.conv2d(_from_e4m3(lo8).double().permute(0, 3, 1, 2), w8, padding=k // 2)) * pc.acc_scale + bias.double().view(1, -1, 1, 1)
+    exact = F.conv2d(x.double(), wgt.double(), bias.double(), padding=k // 2)
+    o = ops.conv_ex(xh, pc, x_lo8=lo8, want_f32=True, want_relu=True, want_relu_lo8=True)
+    single = ops.conv_ex(xh, ops.PackedConv(wgt, bias, 1), want_f32=True)
+    torch.cuda.synchronize()
+    scale = float(exact.abs().max())
+    e_quant = float((_nchw(o.f32).double() - quant).abs().max()) / scale
+    e_exact = float((_nchw(o.f32).double() - exact).abs().max()) / scale
+    e_single = float((_nchw(single.f32).double() - exact).abs().max()) / scale
+    print(f'fp8 correction: vs quantised operands {e_quant:.2e}, vs exact {e_exact:.2e}, single pass vs exact {e_single:.2e}')
+    assert e_quant < 2e-5, e_quant
+    assert e_exact < 0.25 * e_single, (e_exact, e_single)
+    # the e4m3 remainder of the ReLU'd output, as the next layer's low-order operand
+    want = _nchw(o.f32).clamp_min(0)
+    rem = (want - want.half().float()) * 4096.0
+    got = _from_e4m3(o.relu_lo8).permute(0, 3, 1, 2)
+    assert float((got - rem).abs().max()) <= 0.07 * float(rem.abs().max()) + 2 ** -9  # 3-bit mantissa: <= 6.25 % + subnormal step
+
+
+def test_up2_add_split_e4m3_remainder():
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(12)
+    b, h, w, c = 2, 11, 17, 128
+    x = torch.randn(b, h, w, c, device='cuda', generator=g) * 3
+    skip = torch.randn(1, 2 * h, 2 * w, c, device='cuda', generator=g)
+    hi, lo = _split(x)
+    s_hi, s_lo = _split(skip)
+    raw, raw_lo, relu, relu_lo8 = ops.up2_add_split(hi, lo, s_hi, s_lo, want_relu_lo8=True)
+    ref = F.interpolate((hi.float() + lo.float()).permute(0, 3, 1, 2), scale_factor=2, mode='bilinear',
+                        align_corners=False).permute(0, 2, 3, 1) + s_hi.float() + s_lo.float()
+    torch.cuda.synchronize()
+    assert relu_lo8.dtype == torch.uint8
+    want = ref.clamp_min(0)
+    assert float((relu.float() - want).abs().max()) < 4e-3
+    rem = (want - relu.float()) * 4096.0
+    got = _from_e4m3(relu_lo8)
+    assert float((got - rem).abs().max()) <= 0.07 * float(rem.abs().max()) + 2 ** -9 + 0.1  # + fp32 interpolation order
+    assert float((raw.float() + raw_lo.float() - ref).abs().max()) < 2e-5

@@ -169,6 +169,7 @@ DEVA_B200_API int deva_b200_conv2d(const deva_b200_conv_desc* c, deva_stream_t s
   d.out_raw_lo = c->out_raw_lo; d.out_relu_lo = c->out_relu_lo;
   d.head_w = c->head_w; d.head_out = c->head_out; d.head_n = c->head_n;
   d.gate_h = c->gate_h; d.gate_out = c->gate_out; d.ksplit = c->ksplit;
+  d.x_lo8 = c->x_lo8; d.w8_packed = c->w8_packed; d.acc_scale = c->acc_scale; d.out_relu_lo8 = c->out_relu_lo8;
   return launch_conv(d, S(stream));
 }
 DEVA_B200_API int deva_b200_stem_im2col(const float* src, void* dst, void* dst_lo, int b, int c, int h, int w, int k_pad,
@@ -202,10 +203,10 @@ DEVA_B200_API int deva_b200_cbam(const void* x, const float* w1, const float* b1
   return ew_cbam(H(x), w1, b1, w2, b2, ws, bs, scratch, H(raw), H(relu), b, h, w, c, r, S(stream));
 }
 DEVA_B200_API int deva_b200_up2_add_split(const void* g, const void* g_lo, const void* skip, const void* skip_lo,
-                                          void* raw, void* raw_lo, void* relu, void* relu_lo, int b, int h, int w, int c,
-                                          deva_stream_t stream) {
-  return ew_up2_add_split(H(g), H(g_lo), H(skip), H(skip_lo), H(raw), H(raw_lo), H(relu), H(relu_lo), b, h, w, c,
-                          S(stream));
+                                          void* raw, void* raw_lo, void* relu, void* relu_lo, void* relu_lo8, int b, int h,
+                                          int w, int c, deva_stream_t stream) {
+  return ew_up2_add_split(H(g), H(g_lo), H(skip), H(skip_lo), H(raw), H(raw_lo), H(relu), H(relu_lo),
+                          reinterpret_cast<unsigned char*>(relu_lo8), b, h, w, c, S(stream));
 }
 DEVA_B200_API int deva_b200_cbam_split(const void* x, const void* x_lo, const float* w1, const float* b1, const float* w2,
                                        const float* b2, const float* ws, const float* bs, float* scratch, void* raw,

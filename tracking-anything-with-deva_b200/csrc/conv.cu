@@ -77,12 +77,20 @@ struct Params {
   // costs a split-precision conv with a deep K loop ~1e-5 relative (tools/accum_probe.py); short chains do not.
   int ksplit, k_per_split;
   long long f32_split_stride;
+  // fp8 correction entries (split_mode 3): k-entries [0, taps16) are fp16 passes of `cblocks` 64-channel blocks, entries
+  // [taps16, taps) are kind::f8f6f4 (e4m3 x e4m3) passes of `cblocks8` 128-channel blocks over the 8-bit low-order
+  // activation tensor and the 8-bit weights; both feed the same accumulator, which the epilogue scales by acc_scale.
+  int taps16, cblocks8;
+  float acc_scale;
+  uint8_t* out_relu_lo8;  // optional: e4m3 of (relu - fp16(relu)) * 4096, the low-order operand of the next fp8 pass
 };
 
 struct Maps {
   CUtensorMap act[8];
   CUtensorMap wgt;        // box {64, nt}
   CUtensorMap wgt_slice;  // box {64, nt / cs} (cluster multicast)
+  CUtensorMap act8;       // e4m3 low-order activations, box {128 B, tw, th}
+  CUtensorMap wgt8;       // e4m3 weights, box {128 B, nt / cs}
 };
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, const int (&c)[5]) {
@@ -121,6 +129,29 @@ __device__ __forceinline__ void store_split(const float (&v)[32], __half* hi, __
     }
     *reinterpret_cast<uint4*>(hi + off + j) = oh;
     if (lo) *reinterpret_cast<uint4*>(lo + off + j) = ol;
+  }
+}
+
+// 32 fp32 values -> e4m3 of (relu(v) - fp16(relu(v))) * 4096: the 8-bit low-order operand of an fp8 correction pass
+__device__ __forceinline__ void store_lo8(const float (&v)[32], uint8_t* dst) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 16) {
+    uint4 o;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float l[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float a = fmaxf(v[j + 4 * e + t], 0.f);
+        l[t] = (a - __half2float(__float2half_rn(a))) * 4096.f;
+      }
+      uint16_t lo16, hi16;
+      asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo16) : "f"(l[1]), "f"(l[0]));  // {l[1] : high byte, l[0] : low byte}
+      asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi16) : "f"(l[3]), "f"(l[2]));
+      w[e] = (uint32_t)lo16 | ((uint32_t)hi16 << 16);
+    }
+    *reinterpret_cast<uint4*>(dst + j) = o;
   }
 }
 
@@ -183,7 +214,8 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
   const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
   const int total_units = ((p.m_tiles + cs - 1) / cs) * p.n_tiles * p.ksplit;
   const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
-  const int k_iters = p.taps * p.cblocks;
+  const int k16 = p.taps16 * p.cblocks;                       // fp16 k-iterations come first ...
+  const int k_iters = k16 + (p.taps - p.taps16) * p.cblocks8;  // ... then the fp8 correction k-iterations
   // PAIR: both CTAs' loads are credited to the leader's barrier -> it expects the bytes of both
   const uint32_t stage_tx = PAIR ? 2 * (A_BYTES + (p.nt / 2) * BK * 2) : A_BYTES + p.nt * BK * 2;
 
@@ -191,6 +223,8 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
     for (int i = 0; i < 8; ++i) tma_prefetch_desc(&maps.act[i]);
     tma_prefetch_desc(&maps.wgt);
     tma_prefetch_desc(&maps.wgt_slice);
+    tma_prefetch_desc(&maps.act8);
+    tma_prefetch_desc(&maps.wgt8);
     // empty[]: one tcgen05.commit arrive per MMA-issuing CTA that reads the stage (PAIR: the single pair MMA)
     for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], PAIR ? 1 : cs); }
     // acc_empty[]: PAIR -> the leader's barrier collects the epilogue warps of both CTAs
@@ -216,31 +250,34 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
         int b, y0, x0, n0, ks;
         tile_decode(u, rank, p, b, y0, x0, n0, ks);
         const int k_lo = ks * p.k_per_split, k_hi = min(k_iters, k_lo + p.k_per_split);
-        for (int t = k_lo / p.cblocks; t < p.taps && t * p.cblocks < k_hi; ++t) {
-          int c[5] = {0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b, 0};  // (channel, x, y, image, 1)
-          const CUtensorMap* am = &maps.act[p.tap_map[t]];
-          for (int cb = max(0, k_lo - t * p.cblocks); cb < p.cblocks && t * p.cblocks + cb < k_hi; ++cb) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            c[0] = cb * BK;
-            if constexpr (PAIR) {
-              // own pixels + own half of the weight rows, both at the same offsets in either CTA
-              if (rank == 0) mbar_expect_tx(&full[stage], stage_tx);
-              tma_load_5d_2sm(sA + stage * A_BYTES, am, &full[stage], c);
-              tma_load_2d_2sm(sB + stage * B_STRIDE, &maps.wgt_slice, &full[stage],
-                              (p.tap_w[t] * p.cblocks + cb) * BK, n0 + rank * slice_rows);
-            } else {
-              mbar_expect_tx(&full[stage], stage_tx);
-              tma_load_5d(sA + stage * A_BYTES, am, &full[stage], c);
-              if (cs == 1) {
-                tma_load_2d(sB + stage * B_STRIDE, &maps.wgt, &full[stage], (p.tap_w[t] * p.cblocks + cb) * BK, n0);
-              } else {  // this CTA fetches rows [rank*slice, +slice) of the weight tile for the whole cluster
-                tma_load_2d_mcast(sB + stage * B_STRIDE + rank * slice_rows * 128, &maps.wgt_slice, &full[stage],
-                                  (p.tap_w[t] * p.cblocks + cb) * BK, n0 + rank * slice_rows, cmask);
-              }
+        // one k-iteration: activation box of tap t / channel block cb (+ the matching weight columns) into `stage`
+        auto issue = [&](const int t, const int cb, const bool f8) {
+          int c[5] = {f8 ? cb * 128 : cb * BK, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b, 0};  // (channel, x, y, image, 1)
+          const CUtensorMap* am = f8 ? &maps.act8 : &maps.act[p.tap_map[t]];
+          const CUtensorMap* wm = f8 ? &maps.wgt8 : &maps.wgt_slice;
+          const int wcol = f8 ? (p.tap_w[t] * p.cblocks8 + cb) * 128 : (p.tap_w[t] * p.cblocks + cb) * BK;
+          mbar_wait(&empty[stage], phase ^ 1);
+          if constexpr (PAIR) {
+            // own pixels + own half of the weight rows, both at the same offsets in either CTA
+            if (rank == 0) mbar_expect_tx(&full[stage], stage_tx);
+            tma_load_5d_2sm(sA + stage * A_BYTES, am, &full[stage], c);
+            tma_load_2d_2sm(sB + stage * B_STRIDE, wm, &full[stage], wcol, n0 + rank * slice_rows);
+          } else {
+            mbar_expect_tx(&full[stage], stage_tx);
+            tma_load_5d(sA + stage * A_BYTES, am, &full[stage], c);
+            if (cs == 1) {
+              tma_load_2d(sB + stage * B_STRIDE, f8 ? &maps.wgt8 : &maps.wgt, &full[stage], wcol, n0);
+            } else {  // this CTA fetches rows [rank*slice, +slice) of the weight tile for the whole cluster
+              tma_load_2d_mcast(sB + stage * B_STRIDE + rank * slice_rows * 128, wm, &full[stage], wcol,
+                                n0 + rank * slice_rows, cmask);
             }
-            if (++stage == NST) { stage = 0; phase ^= 1; }
           }
-        }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
+        };
+        for (int t = k_lo / p.cblocks; t < p.taps16 && t * p.cblocks < k_hi; ++t)
+          for (int cb = max(0, k_lo - t * p.cblocks); cb < p.cblocks && t * p.cblocks + cb < k_hi; ++cb) issue(t, cb, false);
+        for (int t = p.taps16; t < p.taps; ++t)  // fp8 correction entries (never combined with split-K)
+          for (int cb = 0; cb < p.cblocks8; ++cb) issue(t, cb, true);
       }
     }
   } else if (warp == 1) {
@@ -260,14 +297,24 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * B_STRIDE);
+          if (ki < k16) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            if constexpr (PAIR)
-              umma_f16_2sm(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                           (ki | k) != 0);
-            else
-              umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                       (ki | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              if constexpr (PAIR)
+                umma_f16_2sm(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                             (ki | k) != 0);
+              else
+                umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                         (ki | k) != 0);
+            }
+          } else {  // e4m3 x e4m3: 128 channels of this tap in four K = 32 instructions over the same 128-byte rows
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if constexpr (PAIR)
+                umma_f8_2sm(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, 1);
+              else
+                umma_f8(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, 1);
+            }
           }
           if constexpr (PAIR) umma_commit_2sm(&empty[stage], cmask);  // frees the stage in both CTAs
           else if (cs == 1) umma_commit(&empty[stage]);
@@ -361,6 +408,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       // while chunk c is finished (the residual comes from L2/HBM: ~1 us if waited for in place); the first chunk's
       // residual is requested before the accumulator is even complete.
       const int n_chunks = p.nt / 32;
+      const float acc_scale = p.acc_scale;
       const bool res_pf = res && live && vec_ok && (p.cout % 32 == 0);
       uint32_t r[32];
       uint4 res_cur[4], res_nxt[4];
@@ -376,7 +424,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
         tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * acc_scale;  // 1 unless the operands were pre-scaled (fp8 mode)
         if (c + 1 < n_chunks) {
           tmem_ld_32x32(t_addr + (c + 1) * 32, r);
           if (res_pf && n0 + (c + 2) * 32 <= p.cout) {
@@ -430,6 +478,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
             }
             store_split(v, p.out_raw, p.out_raw_lo, off + c * 32, false);
             store_split(v, p.out_relu, p.out_relu_lo, off + c * 32, true);
+            if (p.out_relu_lo8) store_lo8(v, p.out_relu_lo8 + off + c * 32);
             if constexpr (HEAD) {  // logit head: 9 taps x 32 channels of this chunk, fp32, weights from shared memory
               float rv[32];
 #pragma unroll
@@ -531,13 +580,20 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   const int n_src = (d.x2 || d.x_lo) ? 2 : 1;
   int pass_src[3] = {0, 0, 0}, pass_w[3] = {0, 0, 0}, n_pass = 1, w_groups = 1;
   if (d.x2) { n_pass = 2; pass_src[1] = 1; pass_w[1] = 1; w_groups = 2; }          // cat[x, x2] . [W0 | W1]
-  B200_REQUIRE(d.split_mode >= 0 && d.split_mode <= 2, "conv: split_mode %d unknown", d.split_mode);
+  B200_REQUIRE(d.split_mode >= 0 && d.split_mode <= 3, "conv: split_mode %d unknown", d.split_mode);
   B200_REQUIRE(d.split_mode != 1 || d.x_lo, "conv: split_mode 1 (activation hi/lo) needs x_lo");
   B200_REQUIRE(d.split_mode != 2 || (!d.x_lo && !d.x2), "conv: split_mode 2 (weight hi/lo) takes a single input");
+  B200_REQUIRE(d.split_mode != 3 || (d.x_lo8 && d.w8_packed && !d.x_lo && !d.x2 && d.stride == 1 && d.cin_pad % 128 == 0 &&
+                                     d.ksplit <= 1),
+               "conv: split_mode 3 (fp8 correction pass) needs x_lo8 + w8_packed, stride 1, cin_pad %% 128 == 0, no x_lo / x2 / ksplit");
   if (d.split_mode == 1) { n_pass = 2; pass_src[1] = 1; pass_w[1] = 0; }                    // Xh.W + Xl.W
   else if (d.split_mode == 2) { n_pass = 2; pass_src[1] = 0; pass_w[1] = 1; w_groups = 2; }  // X.Wh + X.Wl
   else if (d.x_lo) { n_pass = 3; pass_src[1] = 1; pass_w[1] = 0; pass_src[2] = 0; pass_w[2] = 1; w_groups = 2; }  // Xh.Wh + Xl.Wh + Xh.Wl
-  p.taps = ktaps * n_pass;
+  p.taps16 = ktaps * n_pass;
+  p.taps = p.taps16 + (d.split_mode == 3 ? ktaps : 0);  // fp8 correction: one more pass, 128 channels per k-iteration
+  p.cblocks8 = d.split_mode == 3 ? d.cin_pad / 128 : 0;
+  p.acc_scale = d.acc_scale != 0.f ? d.acc_scale : 1.f;
+  p.out_relu_lo8 = reinterpret_cast<uint8_t*>(d.out_relu_lo8);
   B200_REQUIRE(p.taps <= kMaxTaps, "conv: too many k-entries (%d)", p.taps);
   const int phases = d.stride == 1 ? 1 : 4;
   bool built[8] = {false, false, false, false, false, false, false, false};
@@ -568,7 +624,7 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   for (int i = 1; i < 8; ++i)  // unused slots still get prefetched: point them at a valid descriptor
     if (!built[i]) maps.act[i] = maps.act[0];
   for (int t = 0; t < p.taps; ++t) {
-    const int pass = t / ktaps, kt = t % ktaps;
+    const int pass = t < p.taps16 ? t / ktaps : 0, kt = t % ktaps;
     const int oy = kt / d.kw - pad, ox = kt % d.kw - pad;  // input offset relative to stride*yo, stride*xo
     int ph = 0, dy = oy, dx = ox;
     if (d.stride == 2) {
@@ -578,7 +634,7 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
       dx = (ox - px) / 2;
     }
     p.tap_map[t] = (signed char)(pass_src[pass] * 4 + ph);
-    p.tap_w[t] = (signed char)(pass_w[pass] * ktaps + kt);
+    p.tap_w[t] = (signed char)(t < p.taps16 ? pass_w[pass] * ktaps + kt : kt);
     p.tap_dy[t] = (signed char)dy;
     p.tap_dx[t] = (signed char)dx;
   }
@@ -649,9 +705,20 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
     return 3;
   }
   if (cs == 1) maps.wgt_slice = maps.wgt;
+  maps.act8 = maps.act[0];
+  maps.wgt8 = maps.wgt;
+  if (d.split_mode == 3) {
+    const uint64_t k8 = (uint64_t)ktaps * d.cin_pad;  // bytes per weight row (cin_pad is a multiple of 128)
+    if (make_tmap_act5_u8(&maps.act8, d.x_lo8, d.cin_pad, d.w, d.h, d.batch, (long long)d.cin_pad, (long long)d.w * d.cin_pad,
+                          (long long)d.h * d.w * d.cin_pad, d.tw, d.th, &err) ||
+        make_tmap_2d(&maps.wgt8, TmapType::U8, d.w8_packed, k8, d.cout_pad, k8, 128, d.nt / cs, &err)) {
+      set_error("conv: %s", err ? err : "fp8 tensor maps");
+      return 3;
+    }
+  }
   // split-K: fp32 output only, one CTA per unit (no clusters)
   p.ksplit = d.ksplit > 1 ? d.ksplit : 1;
-  const int k_iters_total = p.taps * p.cblocks;
+  const int k_iters_total = p.taps16 * p.cblocks + (p.taps - p.taps16) * p.cblocks8;
   if (p.ksplit > 1) {
     B200_REQUIRE(d.out_f32 && !d.out_raw && !d.out_relu && !d.res && !d.rank1_w && !d.head_w && !d.gate_out,
                  "conv: split-K writes fp32 partial sums only (no residual / rank-1 / head / gates / fp16 outputs)");

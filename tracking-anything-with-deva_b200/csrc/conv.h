@@ -39,6 +39,12 @@ struct ConvDesc {
   const void* gate_h;
   void* gate_out;
   int ksplit;            // > 1: split the K loop; out_f32 is [ksplit_effective, batch, ho, wo, cout] partial sums
+  // split_mode 3: D = (X . W16 + Xlo8 . W8) * acc_scale with W16 = fp16(W * 2^S), W8 = e4m3(W * 2^(S-12)),
+  // Xlo8 = e4m3((x - fp16(x)) * 4096), acc_scale = 2^-S: the low-order activation pass on the fp8 tensor-core path
+  const void* x_lo8;     // u8 NHWC [batch, h, w, cin_pad]
+  const void* w8_packed; // u8 [cout_pad, kh*kw*cin_pad]
+  float acc_scale;       // 0 = 1
+  void* out_relu_lo8;    // optional u8 NHWC: e4m3 low-order part of the ReLU'd output (x 4096)
 };
 
 int launch_conv(const ConvDesc& d, cudaStream_t stream);

@@ -5,6 +5,7 @@
 // are coalesced along the channel axis.
 #include <cuda_fp16.h>
 #include <math_constants.h>
+#include <stdint.h>
 
 #include "common.h"
 #include "elementwise.h"
@@ -202,7 +203,8 @@ __device__ __forceinline__ void st8_split(__half* hi, __half* lo, const float (&
 __global__ void __launch_bounds__(256)
 up2_add_split_kernel(const __half* __restrict__ g, const __half* __restrict__ g_lo, const __half* __restrict__ skip,
                      const __half* __restrict__ skip_lo, __half* __restrict__ raw, __half* __restrict__ raw_lo,
-                     __half* __restrict__ relu, __half* __restrict__ relu_lo, int B, int h, int w, int C) {
+                     __half* __restrict__ relu, __half* __restrict__ relu_lo, unsigned char* __restrict__ relu_lo8, int B,
+                     int h, int w, int C) {
   const int H = 2 * h, W = 2 * w, C8 = C / 8;
   const int b = blockIdx.y / H, Y = blockIdx.y - b * H;
   const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.f);
@@ -251,6 +253,22 @@ up2_add_split_kernel(const __half* __restrict__ g, const __half* __restrict__ g_
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
       st8_split(relu + off, relu_lo + off, o);
+    } else if (relu_lo8) {  // low-order part as e4m3 of (x - fp16(x)) * 4096: operand of an fp8 correction pass
+      uint32_t w8[2];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+      st8(relu + off, o, false);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float l[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) l[t] = (o[4 * e + t] - __half2float(__float2half_rn(o[4 * e + t]))) * 4096.f;
+        unsigned short a16, b16;
+        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(a16) : "f"(l[1]), "f"(l[0]));
+        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(b16) : "f"(l[3]), "f"(l[2]));
+        w8[e] = (uint32_t)a16 | ((uint32_t)b16 << 16);
+      }
+      *reinterpret_cast<uint2*>(relu_lo8 + off) = make_uint2(w8[0], w8[1]);
     } else if (relu) {
       st8(relu + off, o, true);
     }
@@ -647,11 +665,13 @@ int ew_up2_add(const __half* g, const __half* skip, __half* raw, __half* relu, i
   return 0;
 }
 int ew_up2_add_split(const __half* g, const __half* g_lo, const __half* skip, const __half* skip_lo, __half* raw,
-                     __half* raw_lo, __half* relu, __half* relu_lo, int B, int h, int w, int C, cudaStream_t s) {
-  B200_REQUIRE(C % 8 == 0 && g_lo && (raw != nullptr) == (raw_lo != nullptr) && (raw || relu) && (!relu_lo || relu),
+                     __half* raw_lo, __half* relu, __half* relu_lo, unsigned char* relu_lo8, int B, int h, int w, int C,
+                     cudaStream_t s) {
+  B200_REQUIRE(C % 8 == 0 && g_lo && (raw != nullptr) == (raw_lo != nullptr) && (raw || relu) && (!relu_lo || relu) &&
+                   (!relu_lo8 || (relu && !relu_lo)),
                "up2_add_split: C %% 8, g_lo, and raw/raw_lo (both or neither) with at least one output are required");
   ew::up2_add_split_kernel<<<dim3(ceil_div(2 * w * (C / 8), 256 * 2), B * 2 * h), 256, 0, s>>>(
-      g, g_lo, skip, skip_lo, raw, raw_lo, relu, relu_lo, B, h, w, C);
+      g, g_lo, skip, skip_lo, raw, raw_lo, relu, relu_lo, relu_lo8, B, h, w, C);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -9,7 +9,8 @@ int ew_stem_im2col(const float* src, __half* dst, __half* dst_lo, int B, int C, 
 int ew_maxpool(const __half* x, const __half* x_lo, __half* y, __half* y_lo, int B, int H, int W, int C, cudaStream_t s);
 int ew_up2_add(const __half* g, const __half* skip, __half* raw, __half* relu, int B, int h, int w, int C, cudaStream_t s);
 int ew_up2_add_split(const __half* g, const __half* g_lo, const __half* skip, const __half* skip_lo, __half* raw,
-                     __half* raw_lo, __half* relu, __half* relu_lo, int B, int h, int w, int C, cudaStream_t s);
+                     __half* raw_lo, __half* relu, __half* relu_lo, unsigned char* relu_lo8, int B, int h, int w, int C,
+                     cudaStream_t s);
 int ew_cbam_split(const __half* x, const __half* x_lo, const float* w1, const float* b1, const float* w2, const float* b2,
                   const float* ws, const float* bs, float* scratch, __half* raw, __half* raw_lo, __half* relu, __half* relu_lo,
                   int B, int H, int W, int C, int R, cudaStream_t s);

@@ -8,7 +8,7 @@
 
 namespace b200 {
 
-enum class TmapType { F16, F32, BF16 };
+enum class TmapType { F16, F32, BF16, U8 };
 
 // Returns 0 on success; on failure returns non-zero and `err` points at a static message.
 int make_tmap_2d(CUtensorMap* out, TmapType type, const void* base, uint64_t inner, uint64_t outer,
@@ -20,6 +20,11 @@ int make_tmap_2d(CUtensorMap* out, TmapType type, const void* base, uint64_t inn
 int make_tmap_act5(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t b,
                    long long stride_w, long long stride_h, long long stride_b, uint32_t box_w, uint32_t box_h,
                    const char** err);
+
+// Same for an 8-bit (e4m3) activation tensor: dims (C bytes, W, H, B, 1), box (128, box_w, box_h, 1, 1), strides in bytes.
+int make_tmap_act5_u8(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t b,
+                      long long stride_w, long long stride_h, long long stride_b, uint32_t box_w, uint32_t box_h,
+                      const char** err);
 
 // General rank-5 fp16 tiled map, 128-byte swizzle: dims / box in elements, strides (dims 1..4) in elements.
 int make_tmap_f16_5d(CUtensorMap* out, const void* base, const uint64_t (&dims)[5], const long long (&strides)[4],

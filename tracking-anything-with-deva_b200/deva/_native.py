@@ -29,7 +29,8 @@ class ConvDesc(ctypes.Structure):
                 ('out_raw', c_void_p), ('out_relu', c_void_p), ('out_f32', c_void_p),
                 ('out_raw_lo', c_void_p), ('out_relu_lo', c_void_p),
                 ('head_w', c_void_p), ('head_out', c_void_p), ('head_n', c_int32),
-                ('gate_h', c_void_p), ('gate_out', c_void_p), ('ksplit', c_int32)]
+                ('gate_h', c_void_p), ('gate_out', c_void_p), ('x_lo8', c_void_p), ('w8_packed', c_void_p),
+                ('acc_scale', ctypes.c_float), ('out_relu_lo8', c_void_p), ('ksplit', c_int32)]
 
 
 _SIGNATURES = {
@@ -80,7 +81,7 @@ _SIGNATURES = {
     'deva_b200_cbam': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'deva_b200_up2_add_split': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                        c_int, c_int, c_int, c_int, c_void_p]),
+                                        c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'deva_b200_cbam_split': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
@@ -275,10 +276,11 @@ def _p(t):
 def conv2d(x, batch, h, w, cin_pad, w_packed, kh, stride, cout, cout_pad, nt, th, tw, bias, x2=None, x_lo=None, res=None,
            res_lo=None, res_broadcast=False, rank1_w=None, rank1_x=None, out_raw=None, out_relu=None, out_f32=None,
            out_raw_lo=None, out_relu_lo=None, head_w=None, head_out=None, head_n=0, gate_h=None, gate_out=None,
-           split_mode=0, ksplit=0):
+           split_mode=0, ksplit=0, x_lo8=None, w8_packed=None, acc_scale=0.0, out_relu_lo8=None):
     d = ConvDesc(_p(x), _p(x2), _p(x_lo), split_mode, batch, h, w, cin_pad, _p(w_packed), kh, kh, stride, cout, cout_pad, nt, th, tw,
                  _p(bias), _p(res), _p(res_lo), int(res_broadcast), _p(rank1_w), _p(rank1_x), _p(out_raw), _p(out_relu),
-                 _p(out_f32), _p(out_raw_lo), _p(out_relu_lo), _p(head_w), _p(head_out), head_n, _p(gate_h), _p(gate_out), ksplit)
+                 _p(out_f32), _p(out_raw_lo), _p(out_relu_lo), _p(head_w), _p(head_out), head_n, _p(gate_h), _p(gate_out), _p(x_lo8), _p(w8_packed), acc_scale,
+                 _p(out_relu_lo8), ksplit)
     _check(lib().deva_b200_conv2d(ctypes.byref(d), _stream()), 'conv2d')
 
 
@@ -316,9 +318,9 @@ def cbam(x, w1, b1, w2, b2, ws, bs, scratch, raw, relu, b, h, w, c, r):
                                 _ptr(raw), _ptr(relu), b, h, w, c, r, _stream()), 'cbam')
 
 
-def up2_add_split(g, g_lo, skip, raw, raw_lo, relu, b, h, w, c, skip_lo=None, relu_lo=None):
+def up2_add_split(g, g_lo, skip, raw, raw_lo, relu, b, h, w, c, skip_lo=None, relu_lo=None, relu_lo8=None):
     _check(lib().deva_b200_up2_add_split(_ptr(g), _ptr(g_lo), _ptr(skip), _ptr(skip_lo), _ptr(raw), _ptr(raw_lo),
-                                         _ptr(relu), _ptr(relu_lo), b, h, w, c, _stream()), 'up2_add_split')
+                                         _ptr(relu), _ptr(relu_lo), _ptr(relu_lo8), b, h, w, c, _stream()), 'up2_add_split')
 
 
 def cbam_split(x, x_lo, w1, b1, w2, b2, ws, bs, scratch, raw, raw_lo, relu, b, h, w, c, r, relu_lo=None):

@@ -53,10 +53,11 @@ class NativeEngine:
             raise RuntimeError(f"deva_b200: DEVA_B200_PRECISION must be 'parity' or 'fast', got {self.precision!r}")
         self.parity = self.precision == 'parity'
         self.key_ksplit = int(os.environ.get('DEVA_B200_KEY_KSPLIT', '8'))
+        self.fp8_lo = os.environ.get('DEVA_B200_FP8_LO', '1') == '1'
         self.plan_override = [tuple(item.split('=')) for item in os.environ.get('DEVA_B200_PLAN', '').split(',') if '=' in item]
         for _, mode in self.plan_override:
-            if mode not in ('precise', 'act_lo', 'w_lo', 'single') or not self.parity:
-                raise RuntimeError('deva_b200: DEVA_B200_PLAN takes substring=precise|act_lo|w_lo|single items (parity plan only)')
+            if mode not in ('precise', 'act_lo', 'act_lo8', 'w_lo', 'single') or not self.parity:
+                raise RuntimeError('deva_b200: DEVA_B200_PLAN takes substring=precise|act_lo|act_lo8|w_lo|single items (parity plan only)')
         self.device = next(iter(sd.values())).device
         # fold BatchNorm and pack the operands on the host (a few hundred tiny device launches otherwise), upload once
         t = LayerTable({k: v.detach().to('cpu', torch.float32) if v.is_floating_point() else v.cpu() for k, v in sd.items()})
@@ -72,10 +73,11 @@ class NativeEngine:
                 if tail in ('skip8', 'skip4', 'ds_x', 'ds_g') or name.endswith('up_16_8.out_conv.ds'):
                     precise = True
             act_lo = self.parity and 'up_8_4.out_conv' in name
+            act_lo8 = act_lo and self.fp8_lo  # the low-order activation pass of up_8_4 on the fp8 path (half the cost)
             w_lo = self.parity and name.endswith('.sensory_compress')
             for pat, mode in self.plan_override:  # experiments: DEVA_B200_PLAN="substring=precise|act_lo|w_lo|single,..."
                 if pat in name and not (name.startswith('pixel_encoder') or name.startswith('key_proj')):
-                    precise, act_lo, w_lo = mode == 'precise', mode == 'act_lo', mode == 'w_lo'
+                    precise, act_lo, w_lo, act_lo8 = mode == 'precise', mode == 'act_lo', mode == 'w_lo', mode == 'act_lo8'
             if name.endswith('.pred'):  # folded into up_8_4.c2's epilogue as a fp32 9-tap head (see decode)
                 self.pred_w = spec.weight[0].permute(1, 2, 0).reshape(9, -1).float().contiguous().to(self.device)  # [tap, cin]
                 self.pred_b = float(spec.bias[0])
@@ -88,8 +90,10 @@ class NativeEngine:
                 P[name] = ops.PackedConv(spec.weight, spec.bias, 1, two_inputs=True, gates=True)
             else:
                 rank1 = spec.weight.shape[1] - 1 if (name.endswith('.sensory_compress') or name.endswith('.su.g4_conv')) else None
+                act_lo8 = act_lo8 and not precise and spec.weight.shape[1] % 128 == 0 and spec.stride == 1 and rank1 is None
                 P[name] = ops.PackedConv(spec.weight, spec.bias, spec.stride, rank1_in=rank1, precise=precise,
-                                         act_lo=act_lo and not precise, w_lo=w_lo and not (precise or act_lo))
+                                         act_lo=act_lo and not (precise or act_lo8), act_lo8=act_lo8,
+                                         w_lo=w_lo and not (precise or act_lo or act_lo8))
         self.P = {k: v.to(self.device) for k, v in P.items()}
         self.trunk_pairs = any(v.takes_lo for k, v in P.items() if k.startswith('mask_encoder.layer')) or \
             os.environ.get('DEVA_B200_ME_PAIRS', '0') == '1'
@@ -188,12 +192,17 @@ class NativeEngine:
     def _C(self, name, x, lo=None, **kw) -> ops.ConvOut:
         """Conv `name` on (x, lo): the low-order part is consumed only when the layer's precision mode takes it."""
         pc = self.P[name]
+        if pc.takes_lo8:  # `lo` is the e4m3 remainder (uint8)
+            return ops.conv_ex(x, pc, x_lo8=lo if lo is not None else torch.zeros(x.shape, dtype=torch.uint8, device=x.device), **kw)
         if pc.takes_lo:
             return ops.conv_ex(x, pc, x_lo=lo if lo is not None else torch.zeros_like(x), **kw)
         return ops.conv_ex(x, pc, **kw)
 
     def _tl(self, name) -> bool:
         return self.P[name].takes_lo
+
+    def _tl8(self, name) -> bool:
+        return self.P[name].takes_lo8
 
     def _fuse_split(self, p, X, g_raw, g_lo, g_relu, g_relu_lo=None):
         """_fuse of the parity plan: the block's residual stream (shortcut, block outputs, CBAM residual) is carried as
@@ -330,11 +339,14 @@ class NativeEngine:
                 o8 = self._C(q + '.c2', y.relu, y.relu_lo, res=short.raw, res_lo=short.raw_lo, want_raw=True, want_lo=True)
                 p8 = o8.raw
                 q = p + '.up_8_4.out_conv'
-                g4_raw, g4_lo, g4_relu, g4_relu_lo = ops.up2_add_split(p8, o8.raw_lo, skip4, skip4_lo, want_relu_lo=tl(q + '.c1'))
-                y4 = self._C(q + '.c1', g4_relu, g4_relu_lo, want_relu=True, want_lo=tl(q + '.c2'))
+                g4_raw, g4_lo, g4_relu, g4_relu_lo = ops.up2_add_split(p8, o8.raw_lo, skip4, skip4_lo, want_relu_lo=tl(q + '.c1'),
+                                                                       want_relu_lo8=self._tl8(q + '.c1'))
+                y4 = self._C(q + '.c1', g4_relu, g4_relu_lo, want_relu=True, want_lo=tl(q + '.c2'),
+                             want_relu_lo8=self._tl8(q + '.c2'))
                 # p4 = c2(...) + g4; the logit conv pred(relu(p4)) (big_modules.py:189-190) is folded in: the epilogue
                 # emits the 9 per-tap dot products in fp32, a 3x3 gather finishes the convolution.
-                o4 = self._C(q + '.c2', y4.relu, y4.relu_lo, res=g4_raw, res_lo=g4_lo, want_raw=True, head_w=self.pred_w)
+                o4 = self._C(q + '.c2', y4.relu, y4.relu_lo8 if self._tl8(q + '.c2') else y4.relu_lo, res=g4_raw, res_lo=g4_lo,
+                             want_raw=True, head_w=self.pred_w)
             else:
                 p16_raw, p16_relu = ops.conv(h, P[p + '.sensory_compress'], rank1_x=last[i:i + step].contiguous(),
                                              res=ro_all[i:i + step].contiguous(), want_raw=True, want_relu=True)

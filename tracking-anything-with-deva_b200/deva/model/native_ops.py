@@ -34,14 +34,17 @@ class PackedConv:
     """One convolution ready for ``deva_b200_conv2d``."""
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int,
                  rank1_in: Optional[int] = None, two_inputs: bool = False, precise: bool = False,
-                 gates: bool = False, act_lo: bool = False, w_lo: bool = False):
+                 gates: bool = False, act_lo: bool = False, w_lo: bool = False, act_lo8: bool = False):
         """weight [Cout, Cin, k, k] fp32 (BN folded); if ``rank1_in`` is given, that input channel is split
         off as a rank-1 term (out += w[:, rank1_in] * x1) - used for the '+1' mask / logit channels.
         ``gates``: Cout = [forget | update | new] x C of a sensory updater; rows are regrouped so that every
         192-channel tile holds the three gates of 64 hidden channels and the conv epilogue applies the update.
         Precision modes (exclusive): ``precise`` = inputs (hi, lo) x weights (hi, lo), three MMA passes, ~fp32;
         ``act_lo`` = inputs (hi, lo) x single fp16 weights, two passes (no activation-operand rounding);
-        ``w_lo`` = single fp16 input x weights (hi, lo), two passes (no weight rounding)."""
+        ``w_lo`` = single fp16 input x weights (hi, lo), two passes (no weight rounding);
+        ``act_lo8`` = like act_lo with the low-order pass on the fp8 path: the activation remainder arrives as e4m3 of
+        (x - fp16(x)) * 4096, the weights are packed twice - fp16(W * 2^S) and e4m3(W * 2^(S-12)) - and the epilogue scales
+        the common accumulator by 2^-S; the correction pass covers 128 channels per k-iteration, i.e. costs half a pass."""
         cout, cin, kh, kw = weight.shape
         self.gates = gates
         if gates:
@@ -61,10 +64,12 @@ class PackedConv:
             cin -= 1
         self.two_inputs = two_inputs
         self.precise = precise  # split precision: weights stored as fp16 (hi, lo), inputs arrive as (hi, lo)
-        self.act_lo, self.w_lo = act_lo, w_lo
-        assert int(precise) + int(act_lo) + int(w_lo) <= 1 and not (two_inputs and (precise or act_lo or w_lo))
-        self.split_mode = 1 if act_lo else (2 if w_lo else 0)
+        self.act_lo, self.w_lo, self.act_lo8 = act_lo, w_lo, act_lo8
+        assert int(precise) + int(act_lo) + int(w_lo) + int(act_lo8) <= 1 and not (two_inputs and (precise or act_lo or w_lo or act_lo8))
+        self.split_mode = 1 if act_lo else (2 if w_lo else (3 if act_lo8 else 0))
         self.takes_lo = precise or act_lo
+        self.takes_lo8 = act_lo8
+        self.w8_packed, self.acc_scale = None, 0.0
         if two_inputs:  # the layer consumes cat[x, x2]: pack [cout, source, tap, cin/2]
             assert cin % 128 == 0 and stride == 1
             cin //= 2
@@ -89,6 +94,14 @@ class PackedConv:
             lo = (w - hi.float()).half()
             w = torch.cat([hi.float(), lo.float()], 1)
             nsrc = 2
+        if act_lo8:
+            assert self.cin_pad % 128 == 0 and stride == 1, 'the fp8 correction pass needs Cin % 128 == 0 and stride 1'
+            import math
+            s_exp = math.floor(math.log2(60000.0 / max(float(w.abs().max()), 1e-30)))
+            self.acc_scale = 2.0 ** (-s_exp)
+            self.w8_packed = (w * 2.0 ** (s_exp - 12)).reshape(self.cout_pad, kh * kw * self.cin_pad) \
+                .to(torch.float8_e4m3fn).view(torch.uint8).contiguous()
+            w = w * 2.0 ** s_exp
         self.w_packed = w.reshape(self.cout_pad, nsrc * kh * kw * self.cin_pad).half().contiguous()
         self.bias = torch.zeros(self.cout_pad, dtype=torch.float32, device=dev)
         if bias is not None:
@@ -101,6 +114,8 @@ class PackedConv:
         """Packing runs where the checkpoint lives (the engine packs on the host); this uploads the packed operands."""
         self.w_packed = self.w_packed.to(device)
         self.bias = self.bias.to(device)
+        if self.w8_packed is not None:
+            self.w8_packed = self.w8_packed.to(device)
         if self.rank1_w is not None:
             self.rank1_w = self.rank1_w.to(device)
         return self
@@ -111,20 +126,24 @@ class PackedConv:
 
 
 class ConvOut:
-    __slots__ = ('raw', 'raw_lo', 'relu', 'relu_lo', 'f32', 'head', 'hidden')
+    __slots__ = ('raw', 'raw_lo', 'relu', 'relu_lo', 'relu_lo8', 'f32', 'head', 'hidden')
 
     def __init__(self):
-        self.raw = self.raw_lo = self.relu = self.relu_lo = self.f32 = self.head = self.hidden = None
+        self.raw = self.raw_lo = self.relu = self.relu_lo = self.relu_lo8 = self.f32 = self.head = self.hidden = None
 
 
 def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = None, x_lo: Optional[torch.Tensor] = None,
             res: Optional[torch.Tensor] = None, res_lo: Optional[torch.Tensor] = None,
             rank1_x: Optional[torch.Tensor] = None, want_raw: bool = False, want_relu: bool = False,
             want_f32: bool = False, want_lo: bool = False, head_w: Optional[torch.Tensor] = None,
-            gate_h: Optional[torch.Tensor] = None, ksplit: int = 0) -> ConvOut:
+            gate_h: Optional[torch.Tensor] = None, ksplit: int = 0, x_lo8: Optional[torch.Tensor] = None,
+            want_relu_lo8: bool = False) -> ConvOut:
     """x fp16 NHWC [B,H,W,cin_pad] (+ x2: implicit channel concat, or + x_lo: split precision) -> ConvOut."""
     assert x.dtype == torch.float16 and x.is_contiguous() and x.shape[-1] == pc.cin_pad, (x.shape, pc.cin_pad)
     assert (x2 is not None) == pc.two_inputs and (x_lo is not None) == pc.takes_lo, (x_lo is None, pc.takes_lo)
+    assert (x_lo8 is not None) == pc.takes_lo8
+    if x_lo8 is not None:
+        assert x_lo8.dtype == torch.uint8 and x_lo8.is_contiguous() and x_lo8.shape == x.shape
     for other in (x2, x_lo):
         if other is not None:
             assert other.dtype == torch.float16 and other.is_contiguous() and other.shape == x.shape
@@ -162,6 +181,7 @@ def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = Non
     if want_relu:
         o.relu = new()
         o.relu_lo = new() if want_lo else None
+        o.relu_lo8 = new(torch.uint8) if want_relu_lo8 else None
     if want_f32:
         o.f32 = new(torch.float32)
         if ksplit > 1:  # fp32 partial sums [parts, b, ho, wo, cout] of a split K loop; the consumer adds them
@@ -193,11 +213,12 @@ def conv_ex(x: torch.Tensor, pc: PackedConv, *, x2: Optional[torch.Tensor] = Non
                x2=x2, x_lo=x_lo, res=res, res_lo=res_lo, res_broadcast=res_b, rank1_w=pc.rank1_w,
                rank1_x=rank1_x if pc.rank1_w is not None else None, out_raw=o.raw, out_relu=o.relu, out_f32=o.f32,
                out_raw_lo=o.raw_lo, out_relu_lo=o.relu_lo, head_w=head_w, head_out=o.head, head_n=head_n,
-               gate_h=gate_h, gate_out=o.hidden, split_mode=pc.split_mode, ksplit=ksplit)
+               gate_h=gate_h, gate_out=o.hidden, split_mode=pc.split_mode, ksplit=ksplit, x_lo8=x_lo8,
+               w8_packed=pc.w8_packed, acc_scale=pc.acc_scale, out_relu_lo8=o.relu_lo8)
     if PROFILE is not None:
         ev1.record()
         flops = 2.0 * b * ho * wo * pc.cout * pc.k * pc.k * pc.cin * (2 if pc.two_inputs else 1)
-        PROFILE.append((ev0, ev1, flops, 3 if pc.precise else (2 if (pc.act_lo or pc.w_lo) else 1)))
+        PROFILE.append((ev0, ev1, flops, 3 if pc.precise else (2 if (pc.act_lo or pc.w_lo) else (1.5 if pc.act_lo8 else 1))))
     return o
 
 
@@ -246,7 +267,7 @@ def up2_add(g: torch.Tensor, skip: torch.Tensor, want_raw=True, want_relu=True):
 
 
 def up2_add_split(g: torch.Tensor, g_lo: torch.Tensor, skip: torch.Tensor, skip_lo: Optional[torch.Tensor] = None,
-                  want_raw: bool = True, want_relu_lo: bool = False):
+                  want_raw: bool = True, want_relu_lo: bool = False, want_relu_lo8: bool = False):
     """(g + g_lo) bilinear x2 + (skip + skip_lo) -> (raw, raw_lo, relu, relu_lo): the residual stream stays a fp16
     hi/lo pair; relu_lo only when the consumer runs a second activation pass."""
     b, h, w, c = g.shape
@@ -256,8 +277,9 @@ def up2_add_split(g: torch.Tensor, g_lo: torch.Tensor, skip: torch.Tensor, skip_
     raw, raw_lo = (new(), new()) if want_raw else (None, None)
     relu = new()
     relu_lo = new() if want_relu_lo else None
-    nat.up2_add_split(g, g_lo, skip, raw, raw_lo, relu, b, h, w, c, skip_lo=skip_lo, relu_lo=relu_lo)
-    return raw, raw_lo, relu, relu_lo
+    relu_lo8 = torch.empty(b, 2 * h, 2 * w, c, dtype=torch.uint8, device=g.device) if want_relu_lo8 else None
+    nat.up2_add_split(g, g_lo, skip, raw, raw_lo, relu, b, h, w, c, skip_lo=skip_lo, relu_lo=relu_lo, relu_lo8=relu_lo8)
+    return raw, raw_lo, relu, (relu_lo8 if want_relu_lo8 else relu_lo)
 
 
 def area_down(x: torch.Tensor, r: int) -> torch.Tensor:
