@@ -83,7 +83,11 @@ DEVA_B200_API int deva_b200_sim_topk(const void* k_hi, const void* k_lo, const f
                        const void* q_hi, const void* q_lo, const float* bsq, int q, int ck, int top_k,
                        void* workspace, int32_t* out_idx, float* out_w, void* affinity, int64_t ld_affinity,
                        float* use_cnt, float* life_cnt, int n_long, int count_long, int count_work, float* out_sim,
-                       deva_stream_t stream);
+                       const int32_t* prev_idx, float* thr_ws, deva_stream_t stream);
+/* prev_idx (optional, with thr_ws: [q] fp32 scratch): out_idx of the PREVIOUS read of the same window (same slot numbering;
+ * may alias out_idx).  Temporal warm start: the similarities of those top_k slots to the current queries bound every
+ * query's k-th best from below, so the streaming top-k inserts only the few candidates above that bound - the result
+ * is unchanged (exact), the epilogue work drops several-fold.  Pass NULL after any compaction / re-numbering. */
 /* out_sim (optional): fp32 [q, 32] raw similarities of the selected slots (descending; -inf beyond top_k) - what a
  * bank-sharded read exchanges between ranks.
  *

@@ -344,6 +344,18 @@ def golden_detections():
     json.dump({'config': cfg, 'states': states}, open(os.path.join(HERE, 'detections.json'), 'w'))
 
 
+def golden_read_memory():
+    """DEVA.read_memory (network.py:72-92), the training-time read: full softmax over T*H*W memory tokens."""
+    torch.manual_seed(5)
+    B, K, CK, CV, T, H, W = 2, 2, 64, 128, 3, 6, 9
+    net = DEVA(dict(CFG, value_dim=CV)).eval()
+    qk, qe = torch.randn(B, CK, H, W), torch.sigmoid(torch.randn(B, CK, H, W))
+    mk, ms = torch.randn(B, CK, T, H, W), 1 + torch.rand(B, 1, T, H, W)
+    mv = torch.randn(B, K, CV, T, H, W)
+    out = net.read_memory(qk, qe, mk, ms, mv)
+    save('read_memory.npz', qk=qk, qe=qe, mk=mk, ms=ms, mv=mv, out=out)
+
+
 def golden_config1():
     """BASELINE configs[0]: the reference's own example clip (example/vos/bmx-trees, 4 frames 854x480, first-frame ids
     {1, 2}) through DEVAInferenceCore.step exactly as evaluation/eval_vos.py:110-198 drives it (generic dataset, size 480,
@@ -387,6 +399,7 @@ def golden_config1():
 
 
 if __name__ == '__main__':
+    golden_read_memory()
     golden_config1()
     golden_spec()
     golden_memory_read()

@@ -281,3 +281,62 @@ def test_scatter_readout_single_rank():
         torch.cuda.synchronize()
         assert got.shape == want.shape
         assert float((got - want).abs().max()) < 1e-5 * float(want.abs().max()) + 1e-6
+
+
+def test_training_time_read_memory_matches_reference(golden_dir):
+    """DEVA.read_memory (reference network.py:72-92: get_affinity without top-k -> readout) through the
+    similarity / row-softmax / dense readout kernels, against the unmodified reference's output on the same tensors."""
+    from deva.model.network import DEVA
+    g = {k: torch.from_numpy(v).cuda() for k, v in np.load(os.path.join(golden_dir, 'read_memory.npz')).items()}
+    cfg = dict(key_dim=64, value_dim=g['mv'].shape[2], pix_feat_dim=512)
+    net = DEVA(cfg).cuda().eval()
+    out = net.read_memory(g['qk'], g['qe'], g['mk'], g['ms'], g['mv'])
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == tuple(g['out'].shape)
+    err = float((out - g['out']).abs().max())
+    assert err < 2e-3 * max(1.0, float(g['out'].abs().max())), err  # fp16 operands of the readout GEMM, fp32 accumulate
+
+
+def test_warm_started_topk_is_exact():
+    """Temporal warm start (prev_idx): the slots selected for the previous frame's queries bound this frame's k-th best
+    similarity from below; the streaming top-k then skips everything under the bound.  The result must be IDENTICAL to
+    the cold read - also when the previous selection is stale, partly invalid or garbage."""
+    nat = _native()
+    n, q, cv = 6000, 700, 128
+    mk, ms, qk, qe, mv = _make(n, q, 1, cv, 5)
+    bank = Bank(nat, mk, ms, mv, lead=3)
+    dev = 'cuda'
+
+    def read(qk_, prev=None):
+        q_hi = torch.empty(q, 2 * CK, dtype=torch.float16, device=dev)
+        q_lo = torch.empty_like(q_hi)
+        bsq = torch.empty(q, device=dev)
+        nat.pack_query(qk_.to(dev).contiguous(), qe.to(dev).contiguous(), q, 1, CK, q, q_hi, q_lo, bsq)
+        ws = torch.empty(nat.simtopk_workspace_bytes(q), dtype=torch.uint8, device=dev)
+        idx = torch.empty(q, 32, dtype=torch.int32, device=dev) if prev is None else prev  # aliasing prev/out is allowed
+        w = torch.empty(q, 32, device=dev)
+        thr = torch.empty(q, device=dev)
+        nat.sim_topk(bank.k_hi, bank.k_lo, bank.neg_s, bank.nw, bank.lead, q_hi, q_lo, bsq, q, CK, 30, ws, idx, w, None, 0,
+                     None, None, 0, False, False, prev_idx=prev, thr_ws=thr)
+        torch.cuda.synchronize()
+        return idx.clone(), w.clone(), thr.clone()
+
+    idx0, _, _ = read(qk)
+    g = torch.Generator().manual_seed(9)
+    qk1 = qk + 0.05 * torch.randn(qk.shape, generator=g)  # "next frame": most of the top-k persists
+    cold_idx, cold_w, _ = read(qk1)
+    warm_idx, warm_w, thr = read(qk1, prev=idx0.clone())
+    assert torch.equal(warm_idx, cold_idx) and torch.equal(warm_w, cold_w)
+    assert bool(torch.isfinite(thr).all())  # every query got a bound
+    # the bound is tight: it sits close under the true k-th best similarity
+    sim = mm.similarity(mk.double(), ms.double(), qk1.double(), qe.double())
+    kth = torch.sort(sim, 0, descending=True)[0][29]
+    assert bool((thr.cpu().double() <= kth + 1e-6).all()) and float((kth - thr.cpu().double()).median()) < 0.5
+    # a very different query (stale selection), out-of-range and lead-slot indices, and pure garbage: still exact
+    qk2 = torch.randn(qk.shape, generator=g)
+    cold2_idx, cold2_w, _ = read(qk2)
+    stale_idx, stale_w, _ = read(qk2, prev=idx0.clone())
+    assert torch.equal(stale_idx, cold2_idx) and torch.equal(stale_w, cold2_w)
+    junk = torch.randint(-5, bank.nw + 50, (q, 32), dtype=torch.int32, generator=g).to(dev)
+    junk_idx, junk_w, _ = read(qk2, prev=junk)
+    assert torch.equal(junk_idx, cold2_idx) and torch.equal(junk_w, cold2_w)

@@ -52,10 +52,10 @@ DEVA_B200_API int deva_b200_sim_topk(const void* k_hi, const void* k_lo, const f
                        const void* q_hi, const void* q_lo, const float* bsq, int q, int ck, int top_k,
                        void* workspace, int32_t* out_idx, float* out_w, void* affinity, int64_t ld_affinity,
                        float* use_cnt, float* life_cnt, int n_long, int count_long, int count_work, float* out_sim,
-                       deva_stream_t stream) {
+                       const int32_t* prev_idx, float* thr_ws, deva_stream_t stream) {
   return launch_sim_topk(H(k_hi), H(k_lo), neg_s, n_window, n_lead, H(q_hi), H(q_lo), bsq, q, ck, top_k, workspace,
                          out_idx, out_w, H(affinity), ld_affinity, use_cnt, life_cnt, n_long, count_long, count_work,
-                         out_sim, S(stream));
+                         out_sim, prev_idx, thr_ws, S(stream));
 }
 DEVA_B200_API int deva_b200_merge_lists(const float* part_val, const int32_t* part_idx, int n_lists, int top_k, int q,
                                         int q_pitch, int32_t* out_idx, float* out_w, float* out_sim,

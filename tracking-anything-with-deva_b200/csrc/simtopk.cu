@@ -48,6 +48,7 @@ struct Params {
   int* part_idx;
   float* dense_out;     // DENSE mode: [q][ld_dense]
   long long ld_dense;
+  const float* thr_floor;  // optional [q]: a lower bound of each query's k-th best similarity (temporal warm start)
 };
 
 // v[j] for a run-time j without spilling v to local memory: 5-level select tree (31 selects).
@@ -202,6 +203,9 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     const int qg = q0 + row;
     const float bsq = (qg < p.q) ? p.bsq[qg] : 0.f;
     const int top_k = p.top_k;
+    // Nothing at or below a valid lower bound of the k-th best similarity can be in the top-k: with the bound taken from
+    // the slots the previous frame selected, only a handful of candidates per query ever reach the insertion path.
+    const float floor_thr = (!DENSE && p.thr_floor && qg < p.q) ? p.thr_floor[qg] : -CUDART_INF_F;
     float* lv = list_val + group * kListCap * BQ;
     int* li = list_idx + group * kListCap * BQ;
     TopK tk;
@@ -254,8 +258,9 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
           // pending candidates in lock-step (1st of every lane, 2nd of every lane, ...): the warp pays for
           // max-per-lane insertions per chunk, not for every distinct column position.
           uint32_t pending = 0;
+          const float gate = fmaxf(tk.thr, floor_thr);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pending |= (v[j] > tk.thr) ? (1u << j) : 0u;
+          for (int j = 0; j < 32; ++j) pending |= (v[j] > gate) ? (1u << j) : 0u;
           while (__any_sync(0xffffffffu, pending != 0)) {
             if (pending) {
               const int j = __ffs(pending) - 1;
@@ -293,8 +298,9 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32)
 merge_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int nsplit, int top_k, int q,
              int qpad, int* __restrict__ out_idx, float* __restrict__ out_w, __half* __restrict__ P, long long ldP,
              float* __restrict__ use_cnt, int n_long, int add_long, int add_work, float* __restrict__ out_sim) {
-  __shared__ float cv[MERGE_WARPS][kMaxSplit * GROUPS * kListCap + 1];  // +1: rows land in different banks
-  __shared__ int ci[MERGE_WARPS][kMaxSplit * GROUPS * kListCap + 1];
+  // row pitch = 4 mod 32: the staging writes of a warp (4 candidates x 8 queries) and the per-warp scans are conflict-free
+  __shared__ float cv[MERGE_WARPS][kMaxSplit * GROUPS * kListCap + 4];
+  __shared__ int ci[MERGE_WARPS][kMaxSplit * GROUPS * kListCap + 4];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x * MERGE_WARPS;
   const int C = nsplit * top_k;
@@ -397,6 +403,54 @@ __global__ void tick_kernel(float* __restrict__ life, int n) {
 
 }  // namespace simtopk
 
+namespace simtopk {
+// Temporal warm start: thr[q] = min over the slots the PREVIOUS read selected for query q of their similarity to the
+// CURRENT query, minus a margin.  The k-th best of the whole window is >= the k-th best of any k of its slots, so this is
+// a valid lower bound; consecutive frames share most of their top-k, so it is tight.  One warp per query, one lane per
+// slot; operands are the hi parts of the packed rows the GEMM uses, evaluated in fp32 with a rigorous allowance for the
+// dropped low-order parts.  Any invalid slot -> -inf (no bound).
+__global__ void __launch_bounds__(256)
+thr_floor_kernel(const int* __restrict__ prev_idx, int top_k, int q, int n_lead, int n_window, int kdim,
+                 const __half* __restrict__ k_hi, const float* __restrict__ neg_s, const __half* __restrict__ q_hi,
+                 const float* __restrict__ bsq, float* __restrict__ thr) {
+  __shared__ float qrow[8][128];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * 8 + w;
+  if (qi >= q) return;
+  // hi parts only (half the L2 traffic): sum (qh+ql)(kh+kl) = sum qh.kh + R with |R| <= sum |qh.kh| * 2^-9.9 since
+  // |ql| <= 2^-11 |qh| and |kl| <= 2^-11 |kh|; the bound is lowered by that much, which keeps it valid.
+  for (int c = lane; c < kdim; c += 32) qrow[w][c] = __half2float(q_hi[(long long)qi * kdim + c]);
+  __syncwarp();
+  float sim = CUDART_INF_F;
+  bool bad = false;
+  if (lane < top_k) {
+    const int n = prev_idx[(long long)qi * kListCap + lane];
+    if (n < n_lead || n >= n_window) {
+      bad = true;
+    } else {
+      const uint4* ph = reinterpret_cast<const uint4*>(k_hi + (long long)n * kdim);
+      float acc = 0.f, mag = 0.f;
+      for (int c8 = 0; c8 < kdim / 8; ++c8) {
+        const uint4 vh = ph[c8];
+        const __half2* h2 = reinterpret_cast<const __half2*>(&vh);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __half22float2(h2[e]);
+          const float t0 = a.x * qrow[w][c8 * 8 + 2 * e], t1 = a.y * qrow[w][c8 * 8 + 2 * e + 1];
+          acc += t0 + t1;
+          mag += fabsf(t0) + fabsf(t1);
+        }
+      }
+      sim = fmaf(neg_s[n], bsq[qi], acc) - mag * (1.f / 512.f);
+    }
+  }
+  bad = __any_sync(0xffffffffu, bad);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sim = fminf(sim, __shfl_xor_sync(0xffffffffu, sim, o));
+  if (lane == 0) thr[qi] = (bad || !(sim == sim)) ? -CUDART_INF_F : sim - 1e-3f * (1.f + fabsf(sim));
+}
+}  // namespace simtopk
+
 static int make_maps(CUtensorMap* m, const __half* q_hi, const __half* q_lo, int q, const __half* k_hi,
                      const __half* k_lo, int n_window, int ck) {
   const char* err = nullptr;
@@ -434,7 +488,8 @@ size_t simtopk_workspace_bytes(int q) {
 int launch_sim_topk(const __half* k_hi, const __half* k_lo, const float* neg_s, int n_window, int n_lead,
                     const __half* q_hi, const __half* q_lo, const float* bsq, int q, int ck, int top_k,
                     void* workspace, int* out_idx, float* out_w, __half* P, long long ldP, float* use_cnt,
-                    float* life_cnt, int n_long, int count_long, int count_work, float* out_sim, cudaStream_t stream) {
+                    float* life_cnt, int n_long, int count_long, int count_work, float* out_sim, const int* prev_idx,
+                    float* thr_ws, cudaStream_t stream) {
   using namespace simtopk;
   B200_REQUIRE(ck == 32 || ck == 64, "simtopk: key_dim %d unsupported (32 or 64)", ck);
   B200_REQUIRE(top_k >= 1 && top_k <= kListCap, "simtopk: top_k %d out of range [1,%d]", top_k, kListCap);
@@ -462,6 +517,13 @@ int launch_sim_topk(const __half* k_hi, const __half* k_lo, const float* neg_s, 
     configured = true;
   }
   if (P) B200_CUDA(cudaMemsetAsync(P, 0, (size_t)q * ldP * sizeof(__half), stream));
+  if (prev_idx) {
+    B200_REQUIRE(thr_ws != nullptr, "simtopk: prev_idx needs the thr_ws scratch ([q] floats)");
+    thr_floor_kernel<<<ceil_div(q, 8), 256, 0, stream>>>(prev_idx, top_k, q, n_lead, n_window, 2 * ck, k_hi, neg_s, q_hi, bsq,
+                                                         thr_ws);
+    B200_LAUNCH_CHECK();
+    p.thr_floor = thr_ws;
+  }
   simtopk_kernel<false><<<dim3(q_tiles, nsplit), THREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
   B200_LAUNCH_CHECK();
   merge_kernel<<<ceil_div(q, MERGE_WARPS), MERGE_WARPS * 32, 0, stream>>>(

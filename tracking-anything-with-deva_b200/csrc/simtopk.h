@@ -18,8 +18,12 @@ size_t simtopk_workspace_bytes(int q);
 int launch_sim_topk(const __half* k_hi, const __half* k_lo, const float* neg_s, int n_window, int n_lead,
                     const __half* q_hi, const __half* q_lo, const float* bsq, int q, int ck, int top_k,
                     void* workspace, int* out_idx, float* out_w, __half* P, long long ldP, float* use_cnt,
-                    float* life_cnt, int n_long, int count_long, int count_work, float* out_sim, cudaStream_t stream);
+                    float* life_cnt, int n_long, int count_long, int count_work, float* out_sim, const int* prev_idx,
+                    float* thr_ws, cudaStream_t stream);
 // out_sim (optional): [q, kListCap] raw similarities of the selected slots (descending), -inf beyond top_k
+// prev_idx (optional, with thr_ws [q]): the out_idx of the previous read of the SAME window (slot numbering unchanged;
+//   may alias out_idx): those slots' similarities to the current queries bound each query's k-th best from below, and
+//   the streaming top-k only inserts candidates above that bound (exact; see thr_floor_kernel).
 
 constexpr int kMaxMergeLists = 16;
 int launch_merge_lists(const float* part_val, const int* part_idx, int n_lists, int top_k, int q, int qpad, int* out_idx,

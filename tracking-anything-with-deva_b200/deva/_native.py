@@ -46,7 +46,7 @@ _SIGNATURES = {
     'deva_b200_simtopk_workspace_bytes': (c_size_t, [c_int]),
     'deva_b200_sim_topk': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
-                                   c_int, c_int, c_int, c_void_p, c_void_p]),
+                                   c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'deva_b200_merge_lists': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
     'deva_b200_sim_dense_softmax': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
@@ -169,11 +169,13 @@ def simtopk_workspace_bytes(q):
 
 
 def sim_topk(k_hi, k_lo, neg_s, n_window, n_lead, q_hi, q_lo, bsq, q, ck, top_k, workspace, out_idx, out_w,
-             affinity, ld_affinity, use_cnt, life_cnt, n_long, count_long, count_work, out_sim=None):
+             affinity, ld_affinity, use_cnt, life_cnt, n_long, count_long, count_work, out_sim=None, prev_idx=None,
+             thr_ws=None):
     _check(lib().deva_b200_sim_topk(_ptr(k_hi), _ptr(k_lo), _ptr(neg_s), n_window, n_lead, _ptr(q_hi), _ptr(q_lo),
                                     _ptr(bsq), q, ck, top_k, _ptr(workspace), _ptr(out_idx), _ptr(out_w),
                                     _ptr(affinity), ld_affinity, _ptr(use_cnt), _ptr(life_cnt), n_long,
-                                    int(count_long), int(count_work), _ptr(out_sim), _stream()), 'sim_topk')
+                                    int(count_long), int(count_work), _ptr(out_sim), _ptr(prev_idx), _ptr(thr_ws),
+                                    _stream()), 'sim_topk')
 
 
 def merge_lists(part_val, part_idx, n_lists, top_k, q, q_pitch, out_idx, out_w, out_sim=None):

@@ -42,6 +42,12 @@ class BucketBank:
         self.cap = _round_up(self.base + work_cap, 8)
         self.lo = self.base
         self.hi = self.base
+        # slot numbering epoch: bumped whenever existing tokens move (compaction, prepend, re-allocation).  The memory
+        # read keeps each query's previous top-k slots per bank (temporal warm start of the streaming top-k) and may only
+        # reuse them while the numbering is unchanged; appends keep it.
+        self.numbering = 0
+        self.read_idx = None   # int32 [q, 32]: slots the last read selected, relative to its window start
+        self.read_key = None
         self._alloc(self.cap)
 
     # ------------------------------------------------------------------ storage
@@ -68,6 +74,7 @@ class BucketBank:
         self.base, self.cap = new_base, new_cap
         self._alloc(new_cap)
         shift = new_base - old_base
+        self.numbering += 1
         self.lo, self.hi = old_lo + shift, old_hi + shift
         for n, t in old.items():
             getattr(self, n)[self.lo:self.hi] = t[old_lo:old_hi]
@@ -123,6 +130,7 @@ class BucketBank:
         if self.lo - n < 0:
             self._grow(max(n, self.base), 0)
         pos = self.lo - n
+        self.numbering += 1
         self._write_tokens(pos, key_rows, None, 1, self.ck, shrinkage, n)
         live = [self.slot_of[o] for o in self.objects]
         for i, slot in enumerate(live):
@@ -133,6 +141,7 @@ class BucketBank:
     def _compact(self, src_idx: torch.Tensor, dst_start: int) -> None:
         """Move tokens src_idx (physical, int32, ascending) to [dst_start, dst_start+len) via scratch copies."""
         n = int(src_idx.numel())
+        self.numbering += 1
         if n == 0:
             return
         for name in ('k_hi', 'k_lo', 'raw_key', 'raw_sel'):

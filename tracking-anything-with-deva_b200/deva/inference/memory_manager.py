@@ -10,6 +10,7 @@ the math runs in the sm_100a kernels behind ``deva._native``:
 
 There is no PyTorch fallback for any of these.
 """
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -53,6 +54,7 @@ class MemoryManager:
         # 'nhwc': match_memory returns fp16 token-major-backed views (what the native NHWC decoder consumes)
         self.readout_layout = 'nchw'
         self.fused_min_work = 16_000_000  # n_window * q above which the fused sparse-affinity readout is used
+        self.warm_start = os.environ.get('DEVA_B200_TOPK_WARM_START', '1') == '1'
         self.work_frames_without_long_term = 16  # bank capacity (frames) when long-term memory is disabled
 
     def _read_long_term_config(self, config: Dict) -> None:
@@ -132,10 +134,11 @@ class MemoryManager:
         else:     # fp32 [K*CV, q]: the reference's layout
             out, out_tok = torch.empty(k_total * self.CV, q, dtype=torch.float32, device=dev), None
         ws = self._buf('topk_ws', (nat.simtopk_workspace_bytes(q), ), torch.uint8, dev)
-        idx = self._buf('topk_idx', (q, nat.LIST_PITCH), torch.int32, dev)
         wgt = self._buf('topk_w', (q, nat.LIST_PITCH), torch.float32, dev)
+        thr_ws = self._buf('topk_thr', (q, ), torch.float32, dev)
         for bank in self._banks.values():
             w0, lead, n_window = bank.window()
+            idx, prev = self._read_slots(bank, q, w0, lead, dev)
             count_work = self.use_long_term
             count_long = self.use_long_term and self.count_long_term_usage and bank.long_size > 0
             # large reads: affinity tiles are generated on chip by the readout kernel; small reads (where its fixed
@@ -148,7 +151,7 @@ class MemoryManager:
             nat.sim_topk(bank.k_hi[w0:], bank.k_lo[w0:], bank.neg_s[w0:], n_window, lead, q_hi, q_lo, bsq, q,
                          self.CK, self.top_k, ws, idx, wgt, aff, ldp,
                          bank.use_cnt[w0:] if count_work else None, bank.life_cnt[w0:] if count_work else None,
-                         bank.base - w0, count_long, count_work)
+                         bank.base - w0, count_long, count_work, prev_idx=prev, thr_ws=thr_ws)
             objs = bank.objects
             if fused:
                 rws = self._buf('readout_ws', (nat.readout_sparse_workspace_bytes(q, n_window), ), torch.uint8, dev)
@@ -171,6 +174,18 @@ class MemoryManager:
         else:
             out = out.view(k_total, self.CV, h, w)
         return {obj: out[i] for obj, i in order.items()}
+
+    def _read_slots(self, bank: BucketBank, q: int, w0: int, lead: int, dev):
+        """(idx buffer of this bank's read, previous selection or None).  Temporal warm start: while the bank's slot
+        numbering is unchanged (appends keep it) the slots selected for each query in the previous frame bound this
+        frame's k-th best similarity from below, and the top-k kernel only inserts candidates above that bound."""
+        key = (bank.numbering, w0, lead, q, self.top_k)
+        if bank.read_idx is None or bank.read_idx.shape[0] != q or bank.read_idx.device != dev:
+            bank.read_idx = torch.empty(q, nat.LIST_PITCH, dtype=torch.int32, device=dev)
+            bank.read_key = None
+        prev = bank.read_idx if (self.warm_start and bank.read_key == key) else None
+        bank.read_key = key
+        return bank.read_idx, prev
 
     def _object_order(self) -> List[int]:
         """Objects in the order they entered memory == temporary-id order of the object manager."""

@@ -158,8 +158,8 @@ class ShardedMemoryManager(MemoryManager):
         peers = self._peers
         peers.local.zero_()  # ordered before every remote add of this read by the candidate all-gather below
         ws = self._buf('topk_ws', (nat.simtopk_workspace_bytes(q), ), torch.uint8, dev)
-        l_idx = self._buf('l_idx', (q, pitch), torch.int32, dev)
         l_w = self._buf('l_w', (q, pitch), torch.float32, dev)
+        thr_ws = self._buf('topk_thr', (q, ), torch.float32, dev)
         l_sim = self._buf('l_sim', (q, pitch), torch.float32, dev)
         g_sel = self._buf('g_sel', (q, pitch), torch.int32, dev)
         g_w = self._buf('g_w', (q, pitch), torch.float32, dev)
@@ -171,9 +171,14 @@ class ShardedMemoryManager(MemoryManager):
             stride = 1 << 24
             assert n_window < stride
             k_loc = min(self.top_k, n_loc)
+            l_idx, prev = self._read_slots(bank, q, w0, lead, dev)  # the LOCAL top-k of the previous frame bounds this one's
+            if bank.read_key is not None and getattr(bank, 'read_k', None) != k_loc:
+                prev = None
+            bank.read_k = k_loc
             if k_loc > 0:
                 nat.sim_topk(bank.k_hi[w0:], bank.k_lo[w0:], bank.neg_s[w0:], n_window, lead, q_hi, q_lo, bsq, q, self.CK,
-                             k_loc, ws, l_idx, l_w, None, 0, None, None, 0, False, False, out_sim=l_sim)
+                             k_loc, ws, l_idx, l_w, None, 0, None, None, 0, False, False, out_sim=l_sim, prev_idx=prev,
+                             thr_ws=thr_ws)
                 g_idx = torch.where(col < k_loc, l_idx + self.rank * stride, torch.full_like(l_idx, -1))
             else:
                 l_sim.fill_(float('-inf'))

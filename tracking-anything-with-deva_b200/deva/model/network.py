@@ -2,9 +2,9 @@
 
 Holds the checkpoint tensors under the reference's own names (so ``state_dict()`` /
 ``load_state_dict()`` / ``load_weights()`` exchange checkpoints with the reference unchanged) and
-runs inference through ``deva.model.engine.Engine``.  Inference only: the training entry points of the
-reference (``read_memory``, ``need_aux`` heads, ``forward(mode, ...)`` dispatch used by DDP) are not part
-of the propagation hot path.
+runs inference through ``deva.model.engine.Engine``.  Inference only: ``read_memory`` (the training-time twin of the
+memory read) is provided forward-only on the same kernels; the ``need_aux`` heads and the ``forward(mode, ...)`` dispatch
+used by DDP training are not part of the propagation hot path.
 """
 from typing import Dict, Iterable, Tuple
 
@@ -85,6 +85,47 @@ class DEVA(nn.Module):
     @torch.no_grad()
     def transform_key(self, feat: torch.Tensor, *, need_sk: bool = True, need_ek: bool = True):
         return self.engine.transform_key(feat, need_sk, need_ek)
+
+    @torch.no_grad()
+    def read_memory(self, query_key: torch.Tensor, query_selection: torch.Tensor, memory_key: torch.Tensor,
+                    memory_shrinkage: torch.Tensor, memory_value: torch.Tensor) -> torch.Tensor:
+        """The reference's training-time read (network.py:72-92 -> memory_utils.get_affinity / readout): full softmax
+        over all memory tokens, no top-k.  query_key/selection [B,CK,H,W], memory_key [B,CK,T,H,W], memory_shrinkage
+        [B,1,T,H,W], memory_value [B,K,CV,T,H,W] -> [B,K,CV,H,W].  Forward only (this engine carries no autograd), on the
+        same kernels as MemoryManager.consolidation: similarity GEMM (split fp16x3) + row softmax + dense readout GEMM."""
+        from deva import _native as nat
+        b_sz, k = memory_value.shape[:2]
+        cv, ck = memory_value.shape[2], query_key.shape[1]
+        h, w = query_key.shape[-2:]
+        q = h * w
+        dev = query_key.device
+        if cv % 128:
+            raise RuntimeError(f'deva_b200: read_memory needs value_dim % 128 == 0 (got {cv})')
+        out = torch.empty(b_sz, k * cv, q, dtype=torch.float32, device=dev)
+        for b in range(b_sz):
+            mk = memory_key[b].reshape(ck, -1).float().contiguous()
+            n = mk.shape[1]
+            ms = memory_shrinkage[b].reshape(-1).float().contiguous()
+            k_hi = torch.zeros(n, 2 * ck, dtype=torch.float16, device=dev)
+            k_lo = torch.zeros_like(k_hi)
+            neg_s, raw_shr = torch.empty(n, device=dev), torch.empty(n, device=dev)
+            raw_key = torch.empty(n, ck, device=dev)
+            nat.pack_keys(mk, None, n, 1, ms, ck, n, k_hi, k_lo, neg_s, raw_key, None, raw_shr)
+            ld = (n + 7) // 8 * 8
+            vals = torch.zeros(k * cv, ld, dtype=torch.float16, device=dev)
+            nat.append_values(memory_value[b].reshape(k * cv, n).float().contiguous(), n, vals, ld, k * cv, n)
+            q_hi = torch.empty(q, 2 * ck, dtype=torch.float16, device=dev)
+            q_lo = torch.empty_like(q_hi)
+            bsq = torch.empty(q, device=dev)
+            nat.pack_query(query_key[b].reshape(ck, q).float().contiguous(), query_selection[b].reshape(ck, q).float().contiguous(),
+                           q, 1, ck, q, q_hi, q_lo, bsq)
+            sim_ws = torch.empty(q, ld, dtype=torch.float32, device=dev)
+            aff = torch.zeros(q, ld, dtype=torch.float16, device=dev)
+            nat.sim_dense_softmax(k_hi, k_lo, neg_s, raw_shr, n, 0, q_hi, q_lo, bsq, q, ck, sim_ws, ld, aff, ld, None)
+            for i in range(0, k, nat.MAX_GROUPS):
+                rows = [j * cv for j in range(i, min(k, i + nat.MAX_GROUPS))]
+                nat.readout(vals, ld, k * cv, rows, rows, cv, aff, ld, n, q, out[b], q)
+        return out.view(b_sz, k, cv, h, w)
 
     @torch.no_grad()
     def encode_mask(self, image: torch.Tensor, ms_features: Iterable[torch.Tensor], h: torch.Tensor,
