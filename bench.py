@@ -267,6 +267,24 @@ def timed(fn, steps, dist_on):
     return ms, wall
 
 
+def pin_to_gpu_numa_node(gpu_index):
+    """Keep this rank's (single, launch-issuing) host thread on the cores next to its GPU: the 8-GPU boxes have two
+    sockets (SCALE topology: GPU0-3 on NUMA 0, GPU4-7 on NUMA 1) and an unpinned rank may issue its ~115 launches per frame
+    across the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cores = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        allowed = cores & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return sorted(allowed)
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch.distributed as dist
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1))
@@ -274,6 +292,7 @@ def run_ours(args):
     dist_on = world > 1
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
+    pin_to_gpu_numa_node(local)
     if dist_on:
         dist.init_process_group('nccl', device_id=device)
     torch.backends.cudnn.benchmark = True
@@ -305,21 +324,25 @@ def run_ours(args):
     for _ in range(2):
         clip.step_e2e()
     ms_e2e, _ = timed(clip.step_e2e, args.steps, dist_on)
-    for _ in range(2):
-        clip.step_e2e_fused_io()
-    ms_e2e_io, _ = timed(clip.step_e2e_fused_io, args.steps, dist_on)
+    ms_e2e_io = 0.0
+    if not args.quick:
+        for _ in range(2):
+            clip.step_e2e_fused_io()
+        ms_e2e_io, _ = timed(clip.step_e2e_fused_io, args.steps, dist_on)
 
     # conv-stack roofline: a separate short pass with CUDA events around every conv launch (not part of `value`)
     from deva.model import native_ops
     precision = getattr(clip.core.network.engine, 'precision', 'n/a')
     conv_roof = None
-    if rank == 0 or wl.get('sharded'):  # a sharded clip steps on every rank (collectives inside the step)
+    if args.quick:
+        conv_ms = conv_flops = mma_flops = 0.0
+    elif rank == 0 or wl.get('sharded'):  # a sharded clip steps on every rank (collectives inside the step)
         if rank == 0:
             native_ops.PROFILE = []
         for _ in range(5):  # exactly one memory frame
             clip.step_resident()
         torch.cuda.synchronize()
-    if rank == 0:
+    if rank == 0 and not args.quick:
         prof, native_ops.PROFILE = native_ops.PROFILE, None
         conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof) / 5
         conv_flops = sum(f for _, _, f, _ in prof) / 5
@@ -345,8 +368,8 @@ def run_ours(args):
             conv_traffic = tr.get(args.workload + '_conv')
         except Exception:
             pass
-        conv_ach = conv_flops / (conv_ms * 1e-3) / 1e12
-        conv_roof = {'kernel': 'conv_kernel (tcgen05 implicit GEMM), all launches of a frame', 'bound': 'tensor',
+        conv_ach = conv_flops / (conv_ms * 1e-3) / 1e12 if not args.quick else 0.0
+        conv_roof = None if args.quick else {'kernel': 'conv_kernel (tcgen05 implicit GEMM), all launches of a frame', 'bound': 'tensor',
                      'achieved': conv_ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': conv_ach / peak,
                      'traffic': conv_traffic, 'ms_per_frame': conv_ms, 'flops_per_frame': conv_flops,
                      'what': 'algorithmic FLOPs 2*B*Ho*Wo*Cout*k*k*Cin per layer (extra split-precision passes NOT counted) / '
@@ -369,7 +392,7 @@ def run_ours(args):
             'roofline_conv': conv_roof,
             'e2e': {'value': frames_per_step * args.steps / (ms_e2e * 1e-3), 'unit': 'frames/s',
                     'h2d_bytes_per_step': h2d * n_clips_rank, 'd2h_bytes_per_step': d2h * n_clips_rank},
-            'e2e_fused_io': {'value': frames_per_step * args.steps / (ms_e2e_io * 1e-3), 'unit': 'frames/s',
+            'e2e_fused_io': None if args.quick else {'value': frames_per_step * args.steps / (ms_e2e_io * 1e-3), 'unit': 'frames/s',
                              'h2d_bytes_per_step': int(wl['h'] * wl['w'] * 3) * n_clips_rank,
                              'd2h_bytes_per_step': d2h * n_clips_rank,
                              'what': 'uint8 frame upload + on-device normalise; fused argmax + id remap (deva.inference.frame_io)'},
@@ -689,6 +712,7 @@ if __name__ == '__main__':
     ap.add_argument('--ref-objects', type=int, default=1,
                     help='objects per sample step of the CPU reference leg (the rest is extrapolated linearly and flagged)')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the host-cores reference leg')
+    ap.add_argument('--quick', action='store_true', help='value + e2e only (no fused-io e2e, no conv roofline pass)')
     ap.add_argument('--workload', default='c3', choices=list(WORKLOADS))
     ap.add_argument('--no-torch-baseline', action='store_true', help='skip the stock-PyTorch-on-GPU comparison pass')
     a = ap.parse_args()

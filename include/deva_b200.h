@@ -245,8 +245,9 @@ DEVA_B200_API int deva_b200_up2_add_split(const void* g, const void* g_lo, const
  * split_mode 3. */
 DEVA_B200_API int deva_b200_cbam_split(const void* x, const void* x_lo, const float* w1, const float* b1, const float* w2,
                                        const float* b2, const float* ws, const float* bs, float* scratch, void* raw,
-                                       void* raw_lo, void* relu, void* relu_lo, int b, int h, int w, int c, int r,
-                                       deva_stream_t stream);
+                                       void* raw_lo, void* relu, void* relu_lo, int pool_lo, int b, int h, int w, int c,
+                                       int r, deva_stream_t stream);
+/* pool_lo: 1 = the gate statistics (channel pooling, per-pixel max / mean) are taken over x + x_lo, 0 = over x only. */
 /* sensory GRU gates (modules.py:145-149): values fp16 [pixels, 3c], h fp16 [pixels, c] -> out fp16 */
 DEVA_B200_API int deva_b200_gru(const void* values, const void* h, void* out, int64_t pixels, int c,
                                 deva_stream_t stream);

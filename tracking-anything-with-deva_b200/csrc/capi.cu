@@ -210,10 +210,10 @@ DEVA_B200_API int deva_b200_up2_add_split(const void* g, const void* g_lo, const
 }
 DEVA_B200_API int deva_b200_cbam_split(const void* x, const void* x_lo, const float* w1, const float* b1, const float* w2,
                                        const float* b2, const float* ws, const float* bs, float* scratch, void* raw,
-                                       void* raw_lo, void* relu, void* relu_lo, int b, int h, int w, int c, int r,
-                                       deva_stream_t stream) {
-  return ew_cbam_split(H(x), H(x_lo), w1, b1, w2, b2, ws, bs, scratch, H(raw), H(raw_lo), H(relu), H(relu_lo), b, h, w, c, r,
-                       S(stream));
+                                       void* raw_lo, void* relu, void* relu_lo, int pool_lo, int b, int h, int w, int c,
+                                       int r, deva_stream_t stream) {
+  return ew_cbam_split(H(x), H(x_lo), w1, b1, w2, b2, ws, bs, scratch, H(raw), H(raw_lo), H(relu), H(relu_lo), pool_lo, b, h,
+                       w, c, r, S(stream));
 }
 DEVA_B200_API int deva_b200_gru(const void* values, const void* h, void* out, int64_t pixels, int c,
                                 deva_stream_t stream) {

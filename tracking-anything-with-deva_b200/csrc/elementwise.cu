@@ -200,77 +200,97 @@ __device__ __forceinline__ void st8_split(__half* hi, __half* lo, const float (&
   *reinterpret_cast<uint4*>(hi) = vh;
   *reinterpret_cast<uint4*>(lo) = vl;
 }
+constexpr int kUpRows = 8;  // output rows walked by one thread: 8 output rows touch 5 source rows, each loaded once
 __global__ void __launch_bounds__(256)
 up2_add_split_kernel(const __half* __restrict__ g, const __half* __restrict__ g_lo, const __half* __restrict__ skip,
                      const __half* __restrict__ skip_lo, __half* __restrict__ raw, __half* __restrict__ raw_lo,
                      __half* __restrict__ relu, __half* __restrict__ relu_lo, unsigned char* __restrict__ relu_lo8, int B,
                      int h, int w, int C) {
+  // blockIdx.y = (image, group of kUpRows output rows).  A thread owns one output column X and 8 channels and walks down
+  // the rows of its group keeping the two source rows it interpolates between (at x0 and x1, hi + lo already summed) in
+  // registers: consecutive output rows share source rows, so each source row is fetched once per group instead of once
+  // per output row (the per-row version re-read the source 5x from DRAM: profiles/r02_ncu_full.md).
   const int H = 2 * h, W = 2 * w, C8 = C / 8;
-  const int b = blockIdx.y / H, Y = blockIdx.y - b * H;
-  const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.f);
-  const int y0 = (int)sy, y1 = min(y0 + 1, h - 1);
-  const float wy = sy - y0;
-  const long long o0 = ((long long)b * h + y0) * w * C, o1 = ((long long)b * h + y1) * w * C;
-  const __half* sk = skip + (long long)Y * W * C;
-  const long long obase = ((long long)b * H + Y) * W * C;
+  const int groups = (H + kUpRows - 1) / kUpRows;
+  const int b = blockIdx.y / groups, Y0 = (blockIdx.y - b * groups) * kUpRows;
   const int row_vecs = W * C8;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < row_vecs; i += gridDim.x * 256) {
     const int X = i / C8, c = (i - X * C8) * 8;
-    const float sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.f);
+    const float sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.f);  // align_corners=False: src = (dst + 0.5)/2 - 0.5, clamped
     const int x0 = (int)sx, x1 = min(x0 + 1, w - 1);
     const float wx = sx - x0;
-    float a[8], bq[8], cq[8], d[8], l[8], o[8], s_[8];
-    ld8(g + o0 + x0 * C + c, a);
-    ld8(g + o0 + x1 * C + c, bq);
-    ld8(g + o1 + x0 * C + c, cq);
-    ld8(g + o1 + x1 * C + c, d);
-    ld8(g_lo + o0 + x0 * C + c, l);
+    float r0a[8], r0b[8], r1a[8], r1b[8], l[8];  // source rows (ya, yb) at columns x0 (a) and x1 (b)
+    int ya = -1, yb = -1;
+    auto load_row = [&](const int y, float (&pa)[8], float (&pb)[8]) {
+      const long long o = (((long long)b * h + y) * w) * C + c;
+      ld8(g + o + (long long)x0 * C, pa);
+      ld8(g_lo + o + (long long)x0 * C, l);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) a[e] += l[e];
-    ld8(g_lo + o0 + x1 * C + c, l);
+      for (int e = 0; e < 8; ++e) pa[e] += l[e];
+      ld8(g + o + (long long)x1 * C, pb);
+      ld8(g_lo + o + (long long)x1 * C, l);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) bq[e] += l[e];
-    ld8(g_lo + o1 + x0 * C + c, l);
+      for (int e = 0; e < 8; ++e) pb[e] += l[e];
+    };
+    for (int Y = Y0; Y < min(H, Y0 + kUpRows); ++Y) {
+      const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.f);
+      const int y0 = (int)sy, y1 = min(y0 + 1, h - 1);
+      const float wy = sy - y0;
+      if (y0 != ya) {
+        if (y0 == yb) {  // the lower row of the previous output row becomes the upper one
 #pragma unroll
-    for (int e = 0; e < 8; ++e) cq[e] += l[e];
-    ld8(g_lo + o1 + x1 * C + c, l);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) d[e] += l[e];
-    ld8(sk + X * C + c, s_);
-    if (skip_lo) {
-      ld8(skip_lo + (long long)Y * W * C + X * C + c, l);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s_[e] += l[e];
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float top = a[e] + (bq[e] - a[e]) * wx, bot = cq[e] + (d[e] - cq[e]) * wx;
-      o[e] = top + (bot - top) * wy + s_[e];
-    }
-    const long long off = obase + X * C + c;
-    if (raw) st8_split(raw + off, raw_lo + off, o);
-    if (relu_lo) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
-      st8_split(relu + off, relu_lo + off, o);
-    } else if (relu_lo8) {  // low-order part as e4m3 of (x - fp16(x)) * 4096: operand of an fp8 correction pass
-      uint32_t w8[2];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
-      st8(relu + off, o, false);
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float l[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) l[t] = (o[4 * e + t] - __half2float(__float2half_rn(o[4 * e + t]))) * 4096.f;
-        unsigned short a16, b16;
-        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(a16) : "f"(l[1]), "f"(l[0]));
-        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(b16) : "f"(l[3]), "f"(l[2]));
-        w8[e] = (uint32_t)a16 | ((uint32_t)b16 << 16);
+          for (int e = 0; e < 8; ++e) { r0a[e] = r1a[e]; r0b[e] = r1b[e]; }
+        } else {
+          load_row(y0, r0a, r0b);
+        }
+        ya = y0;
       }
-      *reinterpret_cast<uint2*>(relu_lo8 + off) = make_uint2(w8[0], w8[1]);
-    } else if (relu) {
-      st8(relu + off, o, true);
+      if (y1 != yb) {
+        if (y1 == ya) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { r1a[e] = r0a[e]; r1b[e] = r0b[e]; }
+        } else {
+          load_row(y1, r1a, r1b);
+        }
+        yb = y1;
+      }
+      float o[8], s_[8];
+      ld8(skip + ((long long)Y * W + X) * C + c, s_);
+      if (skip_lo) {
+        ld8(skip_lo + ((long long)Y * W + X) * C + c, l);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s_[e] += l[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float top = r0a[e] + (r0b[e] - r0a[e]) * wx, bot = r1a[e] + (r1b[e] - r1a[e]) * wx;
+        o[e] = top + (bot - top) * wy + s_[e];
+      }
+      const long long off = (((long long)b * H + Y) * W + X) * C + c;
+      if (raw) st8_split(raw + off, raw_lo + off, o);
+      if (relu_lo) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+        st8_split(relu + off, relu_lo + off, o);
+      } else if (relu_lo8) {  // low-order part as e4m3 of (x - fp16(x)) * 4096: operand of an fp8 correction pass
+        uint32_t w8[2];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+        st8(relu + off, o, false);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float q4[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) q4[t] = (o[4 * e + t] - __half2float(__float2half_rn(o[4 * e + t]))) * 4096.f;
+          unsigned short a16, b16;
+          asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(a16) : "f"(q4[1]), "f"(q4[0]));
+          asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(b16) : "f"(q4[3]), "f"(q4[2]));
+          w8[e] = (uint32_t)a16 | ((uint32_t)b16 << 16);
+        }
+        *reinterpret_cast<uint2*>(relu_lo8 + off) = make_uint2(w8[0], w8[1]);
+      } else if (relu) {
+        st8(relu + off, o, true);
+      }
     }
   }
 }
@@ -670,7 +690,7 @@ int ew_up2_add_split(const __half* g, const __half* g_lo, const __half* skip, co
   B200_REQUIRE(C % 8 == 0 && g_lo && (raw != nullptr) == (raw_lo != nullptr) && (raw || relu) && (!relu_lo || relu) &&
                    (!relu_lo8 || (relu && !relu_lo)),
                "up2_add_split: C %% 8, g_lo, and raw/raw_lo (both or neither) with at least one output are required");
-  ew::up2_add_split_kernel<<<dim3(ceil_div(2 * w * (C / 8), 256 * 2), B * 2 * h), 256, 0, s>>>(
+  ew::up2_add_split_kernel<<<dim3(ceil_div(2 * w * (C / 8), 256), B * ceil_div(2 * h, ew::kUpRows)), 256, 0, s>>>(
       g, g_lo, skip, skip_lo, raw, raw_lo, relu, relu_lo, relu_lo8, B, h, w, C);
   B200_LAUNCH_CHECK();
   return 0;
@@ -710,7 +730,7 @@ int ew_cbam(const __half* x, const float* w1, const float* b1, const float* w2, 
 }
 int ew_cbam_split(const __half* x, const __half* x_lo, const float* w1, const float* b1, const float* w2, const float* b2,
                   const float* ws, const float* bs, float* scratch, __half* raw, __half* raw_lo, __half* relu, __half* relu_lo,
-                  int B, int H, int W, int C, int R, cudaStream_t s) {
+                  int pool_lo, int B, int H, int W, int C, int R, cudaStream_t s) {
   // the gate statistics are pooled over x + x_lo as well: a gate error is common to every channel of a pixel, so it
   // does not average out in the next convolution the way independent roundings do
   B200_REQUIRE(x_lo && raw && raw_lo, "cbam_split: the hi/lo tensors are required");
@@ -719,12 +739,12 @@ int ew_cbam_split(const __half* x, const __half* x_lo, const float* w1, const fl
   float* gate = pmax + (long long)B * ew::kPoolSplit * C;
   float* stats = gate + (long long)B * C;
   const int HW = H * W;
-  ew::cbam_pool_kernel<<<dim3(ceil_div(C, 128), B, ew::kPoolSplit), 128, 0, s>>>(x, x_lo, psum, pmax, HW, C);
+  ew::cbam_pool_kernel<<<dim3(ceil_div(C, 128), B, ew::kPoolSplit), 128, 0, s>>>(x, pool_lo ? x_lo : nullptr, psum, pmax, HW, C);
   B200_LAUNCH_CHECK();
   ew::cbam_mlp_kernel<<<B, 256, (2 * C + 2 * R) * sizeof(float), s>>>(psum, pmax, HW, w1, b1, w2, b2, gate, C, R);
   B200_LAUNCH_CHECK();
   const long long warps = (long long)B * HW;
-  ew::cbam_stats_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, x_lo, gate, stats, B, HW, C);
+  ew::cbam_stats_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, pool_lo ? x_lo : nullptr, gate, stats, B, HW, C);
   B200_LAUNCH_CHECK();
   ew::cbam_apply_split_kernel<<<ceil_div(warps * 32, 256), 256, 0, s>>>(x, x_lo, gate, stats, ws, bs, raw, raw_lo, relu,
                                                                         relu_lo, B, H, W, C);

@@ -13,7 +13,7 @@ int ew_up2_add_split(const __half* g, const __half* g_lo, const __half* skip, co
                      cudaStream_t s);
 int ew_cbam_split(const __half* x, const __half* x_lo, const float* w1, const float* b1, const float* w2, const float* b2,
                   const float* ws, const float* bs, float* scratch, __half* raw, __half* raw_lo, __half* relu, __half* relu_lo,
-                  int B, int H, int W, int C, int R, cudaStream_t s);
+                  int pool_lo, int B, int H, int W, int C, int R, cudaStream_t s);
 int ew_area_down(const __half* x, __half* y, int B, int H, int W, int C, int r, cudaStream_t s);
 int ew_area_down_plane(const float* x, float* y, int B, int H, int W, int r, cudaStream_t s);
 int ew_cbam(const __half* x, const float* w1, const float* b1, const float* w2, const float* b2, const float* ws,

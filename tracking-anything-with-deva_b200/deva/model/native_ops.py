@@ -3,6 +3,7 @@
 Activations are fp16 NHWC torch tensors [B, H, W, C]; weights are packed once per checkpoint into the
 layout the implicit-GEMM kernel streams with TMA ([Cout_pad, taps * Cin_pad] fp16, BN folded bias fp32).
 """
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -309,6 +310,9 @@ def cbam_residual(x: torch.Tensor, params: dict, want_raw=True, want_relu=True):
     return raw, relu
 
 
+CBAM_POOL_LO = os.environ.get('DEVA_B200_CBAM_POOL_LO', '1') == '1'
+
+
 def cbam_residual_split(x: torch.Tensor, x_lo: torch.Tensor, params: dict, want_relu_lo: bool = False):
     """(x + x_lo) + CBAM(x + x_lo) -> (raw, raw_lo, relu, relu_lo)."""
     b, h, w, c = x.shape
@@ -317,7 +321,7 @@ def cbam_residual_split(x: torch.Tensor, x_lo: torch.Tensor, params: dict, want_
     raw, raw_lo, relu = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
     relu_lo = torch.empty_like(x) if want_relu_lo else None
     nat.cbam_split(x, x_lo, params['w1'], params['b1'], params['w2'], params['b2'], params['ws'], params['bs'], scratch,
-                   raw, raw_lo, relu, b, h, w, c, r, relu_lo=relu_lo)
+                   raw, raw_lo, relu, b, h, w, c, r, relu_lo=relu_lo, pool_lo=CBAM_POOL_LO)
     return raw, raw_lo, relu, relu_lo
 
 
