@@ -399,8 +399,19 @@ def run_ours(args):
             'gpu_launches': int(launches), 'wall_ms_per_step': wall / args.steps, 'clocks': clocks,
             'precision_plan': precision,
         }
-        del clip  # give the baseline legs the device
-        torch.cuda.empty_cache()
+    # everything below runs without the clip: give the legs the device
+    del clip
+    torch.cuda.empty_cache()
+    c5 = None
+    if dist_on and args.workload == 'c3' and not args.quick and not args.no_c5_leg:
+        # BASELINE configs[4] on the same ranks: the bank-sharded single video (workload c5) as a second process group of
+        # child processes, one per rank, so that a failure or a hang there can never take the c3 line with it.
+        c5 = _run_dist_leg(['--workload', 'c5', '--quick', '--steps', '10', '--warmup', '3', '--no-c5-leg'], timeout=240)
+    if rank == 0:
+        if c5 is not None:
+            out['bank_sharded_c5'] = c5 if 'error' in c5 else {
+                k: c5.get(k) for k in ('value', 'unit', 'n_gpus', 'steps', 'ms_per_step', 'scaling', 'config', 'roofline', 'e2e',
+                                       'gpu_launches', 'precision_plan')}
         if world == 1 and not args.no_cpu_baseline:
             try:  # bounded sample: 1 warm-up + 2 timed sample steps of the unmodified reference on the host cores
                 leg = _run_leg(['--impl', 'reference', '--steps', '2', '--warmup', '1', '--workload', args.workload,
@@ -674,6 +685,33 @@ def _run_leg(args_list, timeout):
     raise RuntimeError(f'leg {args_list} printed no JSON (rc {r.returncode}): {r.stderr[-300:]}')
 
 
+def _run_dist_leg(args_list, timeout):
+    """Every rank of a torchrun launch calls this: each starts ONE child of this script with its own RANK / LOCAL_RANK /
+    WORLD_SIZE and the next rendezvous port, so the children form their own process group (rank 0's child hosts the store:
+    the elastic agent's variables are dropped).  Returns the child's JSON line on rank 0 ({'error': ...} when the leg
+    failed or timed out), None elsewhere.  Never raises."""
+    rank = int(os.environ.get('RANK', 0))
+    env = {k: v for k, v in os.environ.items() if not k.startswith('TORCHELASTIC')}
+    env['MASTER_ADDR'] = os.environ.get('MASTER_ADDR', '127.0.0.1')
+    env['MASTER_PORT'] = str(int(os.environ.get('MASTER_PORT', '29500')) + 1)
+    cmd = [sys.executable, os.path.abspath(__file__)] + args_list
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    except subprocess.TimeoutExpired:
+        return {'error': f'timed out after {timeout} s'} if rank == 0 else None
+    except Exception as exc:
+        return {'error': f'{type(exc).__name__}: {exc}'[:300]} if rank == 0 else None
+    if rank != 0:
+        return None
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith('{'):
+            try:
+                return json.loads(line)
+            except Exception:
+                break
+    return {'error': f'no JSON line (rc {r.returncode}): {r.stderr[-300:]}'}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1))
     if rank != 0:
@@ -715,6 +753,8 @@ if __name__ == '__main__':
     ap.add_argument('--quick', action='store_true', help='value + e2e only (no fused-io e2e, no conv roofline pass)')
     ap.add_argument('--workload', default='c3', choices=list(WORKLOADS))
     ap.add_argument('--no-torch-baseline', action='store_true', help='skip the stock-PyTorch-on-GPU comparison pass')
+    ap.add_argument('--no-c5-leg', action='store_true',
+                    help='N > 1 only: skip the bank-sharded single-video leg (workload c5 on the same ranks, key bank_sharded_c5)')
     a = ap.parse_args()
     if a.impl == 'reference':
         run_reference(a)

@@ -186,7 +186,7 @@ def test_conv_rank1_term():
     assert float((_nchw(out) - ref).abs().max()) < 2e-3
 
 
-@pytest.mark.parametrize('k_obj,h,w', [(1, 32, 48), (3, 48, 80)])
+@pytest.mark.parametrize('k_obj,h,w', [(1, 32, 48), (3, 48, 80), (2, 44, 520)])  # last: ragged row group / column block
 def test_stem_matches_torch(k_obj, h, w):
     """7x7 s2 stem = shared image part (3 ch) + per-object mask part (1 ch), both through im2col + 1x1 GEMM."""
     ops = _ops()

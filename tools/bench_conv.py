@@ -17,6 +17,10 @@ CASES = {
     'up168_c1': (16, 136, 240, 512, 256, 3, 'relu'),
     'ds_1x1': (16, 136, 240, 512, 256, 1, 'raw'),
     'res2_c3_precise': (1, 272, 480, 64, 256, 1, 'precise'),
+    # shallow-K layers (epilogue / latency bound): sensory updater 1x1 convs, the mask stem as a 1x1 GEMM over 64 im2col columns
+    'g16_1x1': (16, 68, 120, 512, 512, 1, 'raw'),
+    'g8_1x1_res': (16, 68, 120, 256, 512, 1, 'raw+res'),
+    'stem_1x1': (16, 544, 960, 64, 64, 1, 'relu'),
 }
 
 

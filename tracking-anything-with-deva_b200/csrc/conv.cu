@@ -111,33 +111,53 @@ __device__ __forceinline__ void tma_load_5d_2sm(void* smem_dst, const CUtensorMa
       : "memory");
 }
 
-// 32 fp32 values -> fp16 (and optionally the fp16 remainder value - fp16(value)), 16-byte stores
-__device__ __forceinline__ void store_split(const float (&v)[32], __half* hi, __half* lo, long long off, bool relu) {
-  if (!hi) return;
+// 32 fp32 values -> fp16 (and optionally the fp16 remainder value - fp16(value)).  `wide`: the destination is 32-byte
+// aligned (Cout % 16 == 0) -> 256-bit stores (full sectors, half the LSU instructions); otherwise 16-byte stores.
+template <bool WANT_LO>
+__device__ __forceinline__ void store_split_t(const float (&v)[32], __half* hi, __half* lo, long long off, bool relu, bool wide) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    uint4 oh, ol;
-    __half2* h2 = reinterpret_cast<__half2*>(&oh);
-    __half2* l2 = reinterpret_cast<__half2*>(&ol);
+  for (int j = 0; j < 32; j += 16) {
+    uint4 oh[2], ol[2];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float a = relu ? fmaxf(v[j + 2 * e], 0.f) : v[j + 2 * e];
-      const float b = relu ? fmaxf(v[j + 2 * e + 1], 0.f) : v[j + 2 * e + 1];
-      h2[e] = __floats2half2_rn(a, b);
-      const float2 back = __half22float2(h2[e]);
-      l2[e] = __floats2half2_rn(a - back.x, b - back.y);
+    for (int g = 0; g < 2; ++g) {
+      __half2* h2 = reinterpret_cast<__half2*>(&oh[g]);
+      __half2* l2 = reinterpret_cast<__half2*>(&ol[g]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = relu ? fmaxf(v[j + 8 * g + 2 * e], 0.f) : v[j + 8 * g + 2 * e];
+        const float b = relu ? fmaxf(v[j + 8 * g + 2 * e + 1], 0.f) : v[j + 8 * g + 2 * e + 1];
+        h2[e] = __floats2half2_rn(a, b);
+        if (WANT_LO) {
+          const float2 back = __half22float2(h2[e]);
+          l2[e] = __floats2half2_rn(a - back.x, b - back.y);
+        }
+      }
     }
-    *reinterpret_cast<uint4*>(hi + off + j) = oh;
-    if (lo) *reinterpret_cast<uint4*>(lo + off + j) = ol;
+    if (wide) {
+      stg256(hi + off + j, oh[0], oh[1]);
+      if (WANT_LO) stg256(lo + off + j, ol[0], ol[1]);
+    } else {
+      *reinterpret_cast<uint4*>(hi + off + j) = oh[0];
+      *reinterpret_cast<uint4*>(hi + off + j + 8) = oh[1];
+      if (WANT_LO) {
+        *reinterpret_cast<uint4*>(lo + off + j) = ol[0];
+        *reinterpret_cast<uint4*>(lo + off + j + 8) = ol[1];
+      }
+    }
   }
+}
+__device__ __forceinline__ void store_split(const float (&v)[32], __half* hi, __half* lo, long long off, bool relu, bool wide) {
+  if (!hi) return;
+  if (lo) store_split_t<true>(v, hi, lo, off, relu, wide);
+  else store_split_t<false>(v, hi, lo, off, relu, wide);
 }
 
 // 32 fp32 values -> e4m3 of (relu(v) - fp16(relu(v))) * 4096: the 8-bit low-order operand of an fp8 correction pass
-__device__ __forceinline__ void store_lo8(const float (&v)[32], uint8_t* dst) {
+__device__ __forceinline__ void store_lo8(const float (&v)[32], uint8_t* dst, bool wide) {
+  uint4 o[2];
 #pragma unroll
   for (int j = 0; j < 32; j += 16) {
-    uint4 o;
-    uint32_t* w = reinterpret_cast<uint32_t*>(&o);
+    uint32_t* w = reinterpret_cast<uint32_t*>(&o[j / 16]);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float l[4];
@@ -151,7 +171,23 @@ __device__ __forceinline__ void store_lo8(const float (&v)[32], uint8_t* dst) {
       asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi16) : "f"(l[3]), "f"(l[2]));
       w[e] = (uint32_t)lo16 | ((uint32_t)hi16 << 16);
     }
-    *reinterpret_cast<uint4*>(dst + j) = o;
+  }
+  if (wide) {
+    stg256(dst, o[0], o[1]);
+  } else {
+    *reinterpret_cast<uint4*>(dst) = o[0];
+    *reinterpret_cast<uint4*>(dst + 16) = o[1];
+  }
+}
+
+// 32 consecutive halves (64 bytes) -> four 16-byte registers
+__device__ __forceinline__ void load_res32(const __half* src, uint4 (&r)[4], bool wide) {
+  if (wide) {
+    ldg256(src, r[0], r[1]);
+    ldg256(src + 16, r[2], r[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j] = *reinterpret_cast<const uint4*>(src + j * 8);
   }
 }
 
@@ -330,6 +366,8 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
     const int row = quad * 32 + lane;  // pixel within the tile
     const int ty = row / p.tw, tx = row - ty * p.tw;
     const bool vec_ok = (p.cout % 8) == 0;
+    const bool wide = (p.cout % 16) == 0;   // 32-byte aligned channel chunks: 256-bit loads / stores
+    const bool wide8 = (p.cout % 32) == 0;  // same for the 1-byte e4m3 output
     if constexpr (HEAD) {  // stage the head weights once per CTA (epilogue warps only), zero padded
       for (int i = threadIdx.x - 64; i < kMaxHead * 256; i += 128) {
         const int t = i / 256, ch = i - t * 256;
@@ -364,16 +402,14 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
           tmem_ld_32x32(t_addr + 64 + c * 32, ru);
           tmem_ld_32x32(t_addr + 128 + c * 32, rn);
           uint4 hv[4];
-          if (live) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) hv[j] = *reinterpret_cast<const uint4*>(p.gate_h + hoff + c * 32 + j * 8);
-          }
+          if (live) load_res32(p.gate_h + hoff + c * 32, hv, true);  // gate_c % 64 == 0: always 32-byte aligned
           tmem_ld_wait();
           if (live) {
             const float* bf = p.bias + n0 + c * 32;
+            uint4 ovs[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              uint4 ov;
+              uint4& ov = ovs[j];
               __half2* o2 = reinterpret_cast<__half2*>(&ov);
               const __half2* h2 = reinterpret_cast<const __half2*>(&hv[j]);
 #pragma unroll
@@ -390,8 +426,9 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
                 }
                 o2[e] = __floats2half2_rn(o[0], o[1]);
               }
-              *reinterpret_cast<uint4*>(p.gate_out + hoff + c * 32 + j * 8) = ov;
             }
+            stg256(p.gate_out + hoff + c * 32, ovs[0], ovs[1]);
+            stg256(p.gate_out + hoff + c * 32 + 16, ovs[2], ovs[3]);
           }
         }
         tc_fence_before();
@@ -412,10 +449,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       const bool res_pf = res && live && vec_ok && (p.cout % 32 == 0);
       uint32_t r[32];
       uint4 res_cur[4], res_nxt[4];
-      if (res_pf && n0 + 32 <= p.cout) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) res_cur[j] = *reinterpret_cast<const uint4*>(res + j * 8);
-      }
+      if (res_pf && n0 + 32 <= p.cout) load_res32(res, res_cur, wide);
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + acc * 256;
@@ -427,10 +461,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * acc_scale;  // 1 unless the operands were pre-scaled (fp8 mode)
         if (c + 1 < n_chunks) {
           tmem_ld_32x32(t_addr + (c + 1) * 32, r);
-          if (res_pf && n0 + (c + 2) * 32 <= p.cout) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) res_nxt[j] = *reinterpret_cast<const uint4*>(res + (c + 1) * 32 + j * 8);
-          }
+          if (res_pf && n0 + (c + 2) * 32 <= p.cout) load_res32(res + (c + 1) * 32, res_nxt, wide);
         }
         const int ch0 = n0 + c * 32;
         if (live && ch0 < p.cout) {
@@ -464,9 +495,11 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
               }
             }
             if (res_lo) {
+              uint4 rl[4];
+              load_res32(res_lo + c * 32, rl, wide);
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(res_lo + c * 32 + j);
+                const uint4 rv = rl[j / 8];
                 const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -476,9 +509,9 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
                 }
               }
             }
-            store_split(v, p.out_raw, p.out_raw_lo, off + c * 32, false);
-            store_split(v, p.out_relu, p.out_relu_lo, off + c * 32, true);
-            if (p.out_relu_lo8) store_lo8(v, p.out_relu_lo8 + off + c * 32);
+            store_split(v, p.out_raw, p.out_raw_lo, off + c * 32, false, wide);
+            store_split(v, p.out_relu, p.out_relu_lo, off + c * 32, true, wide);
+            if (p.out_relu_lo8) store_lo8(v, p.out_relu_lo8 + off + c * 32, wide8);
             if constexpr (HEAD) {  // logit head: 9 taps x 32 channels of this chunk, fp32, weights from shared memory
               float rv[32];
 #pragma unroll
@@ -501,7 +534,12 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
             if (p.out_f32) {
               float* o32 = p.out_f32 + ks * p.f32_split_stride + off + c * 32;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int j = 0; j < 32; j += 8) {  // Cout % 8 == 0 on this path: the fp32 rows are 32-byte aligned
+                uint4 a, b;
+                a.x = __float_as_uint(v[j]); a.y = __float_as_uint(v[j + 1]); a.z = __float_as_uint(v[j + 2]); a.w = __float_as_uint(v[j + 3]);
+                b.x = __float_as_uint(v[j + 4]); b.y = __float_as_uint(v[j + 5]); b.z = __float_as_uint(v[j + 6]); b.w = __float_as_uint(v[j + 7]);
+                stg256(o32 + j, a, b);
+              }
             }
           } else {  // ragged channel tail (e.g. Cout = 1, 129): scalar path
 #pragma unroll

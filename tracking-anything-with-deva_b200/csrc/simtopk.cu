@@ -36,7 +36,10 @@ constexpr int Q_BYTES = 2 * MAX_KB * QTILE_BYTES;  // hi/lo x k-blocks
 constexpr int KSTAGE_BYTES = 2 * MAX_KB * KTILE_BYTES;
 constexpr int LIST_BYTES = GROUPS * 2 * kListCap * BQ * 4;
 constexpr int NS_BYTES = ACC_STAGES * BNK * 4;
-constexpr int SMEM_BYTES = Q_BYTES + KSTAGES * KSTAGE_BYTES + LIST_BYTES + NS_BYTES + 256 + 1024;
+static_assert(GROUPS == 2, "the threshold exchange pairs group g with group g ^ 1");
+constexpr int THR_BYTES = GROUPS * BQ * 4;  // each epilogue group publishes its running k-th best per query
+constexpr int SMEM_BYTES = Q_BYTES + KSTAGES * KSTAGE_BYTES + LIST_BYTES + NS_BYTES + 256 + THR_BYTES;
+static_assert(SMEM_BYTES <= 232448, "simtopk: shared-memory budget");
 
 struct Params {
   int q, n_window, n_lead, kblocks, top_k;
@@ -123,6 +126,7 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
   uint64_t* acc_full = empty + KSTAGES;         // [ACC_STAGES]
   uint64_t* acc_empty = acc_full + ACC_STAGES;  // [ACC_STAGES]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+  volatile float* thr_pub = reinterpret_cast<volatile float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [GROUPS][BQ]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -220,7 +224,14 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
         tk.gpos[i] = i * 8;
       }
       tk.refresh();
+      // The two groups scan alternating tiles of the SAME queries into separate lists.  Each publishes its running k-th
+      // best; the other group's value is a valid lower bound of the query's global k-th best (its list holds k real
+      // candidates at least that large), so gating on it keeps every global top-k member while cutting the insertions
+      // of two half-length lists to about those of one full-length list.  Stale reads are fine: the bound only grows.
+      thr_pub[group * BQ + row] = -CUDART_INF_F;
+      named_bar_sync(3, GROUPS * 128);
     }
+    volatile const float* thr_other = thr_pub + (group ^ 1) * BQ + row;
     for (int it = group; t_begin + it < t_end; it += GROUPS) {
       const int acc = it & (ACC_STAGES - 1);
       const int n0 = (t_begin + it) * BNK;
@@ -258,7 +269,7 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
           // pending candidates in lock-step (1st of every lane, 2nd of every lane, ...): the warp pays for
           // max-per-lane insertions per chunk, not for every distinct column position.
           uint32_t pending = 0;
-          const float gate = fmaxf(tk.thr, floor_thr);
+          const float gate = fmaxf(fmaxf(tk.thr, floor_thr), *thr_other);
 #pragma unroll
           for (int j = 0; j < 32; ++j) pending |= (v[j] > gate) ? (1u << j) : 0u;
           while (__any_sync(0xffffffffu, pending != 0)) {
@@ -269,6 +280,7 @@ simtopk_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
               if (x > tk.thr) tk.insert(lv, li, row, x, n0 + c * 32 + j);
             }
           }
+          thr_pub[group * BQ + row] = tk.thr;
         }
       }
       tc_fence_before();

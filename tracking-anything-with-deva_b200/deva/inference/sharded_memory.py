@@ -95,6 +95,12 @@ class PeerBuffers:
             nat.peer_free(self.device.index, self._own)
             self._own = 0
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: the driver reclaims the allocation with the context
+            pass
+
 
 class ShardedBankReader:
     """Holds one rank's shard (packed keys + values) and performs the distributed read."""
@@ -201,6 +207,9 @@ class ShardedBankReader:
         per = -(-self.k // self.world)
         peers = self._scratch.get('peers')
         if peers is None or peers.local.shape[1] != q:
+            if peers is not None:  # the query count changed: release the old allocation and its IPC mappings first
+                torch.cuda.synchronize(self.dev)
+                peers.close()
             peers = PeerBuffers((per * self.cv, q), self.dev, self.group)
             self._scratch['peers'] = peers
         peers.local.zero_()  # ordered before every remote add of this read by the all-gather below
@@ -245,6 +254,9 @@ class ShardedBankReader:
                                            idx_loc, w_loc, pitch, self.n, q, rws, peers.ptrs, q)
         if self.world > 1:  # every rank's adds have been issued and completed before anyone consumes its buffer
             fence = self._buf('fence', (1, ), torch.float32)
+            fence.zero_()
             dist.all_reduce(fence, group=self.group)
         lo, hi = self.objects_of(self.rank)
+        # Lifetime: a view of the peer buffer, valid until the NEXT read_scatter of this reader (which zeroes it and lets
+        # the peers add into it again); consume it on the current stream before then, or clone it.
         return peers.local[:(hi - lo) * self.cv]
