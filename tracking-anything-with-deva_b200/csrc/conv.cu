@@ -16,8 +16,8 @@
 // Epilogue (TMEM -> registers): + bias (folded BatchNorm), + optional residual (own or batch-broadcast),
 //   + optional rank-1 term w1[cout] * x1[b, pixel] (the "+1" mask / logit input channel of
 //   sensory_compress and g4_conv), then writes any of: raw fp16, ReLU'd fp16, raw fp32.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..5 = epilogue.  Persistent CTAs, 4-stage
-//   smem ring (6-stage in CTA-pair mode), double-buffered accumulators.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = epilogue (two warps per TMEM lane quadrant, even /
+//   odd 32-column chunks).  Persistent CTAs, 4-stage smem ring (6-stage in CTA-pair mode), double-buffered accumulators.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -40,9 +40,20 @@ constexpr int PAIR_STAGES = 6;
 constexpr int PAIR_STAGE_BYTES = A_BYTES + B_BYTES_MAX / 2;
 static_assert(PAIR_STAGES * PAIR_STAGE_BYTES == STAGES * STAGE_BYTES, "both modes share one shared-memory layout");
 constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-constexpr int THREADS = 192;
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue.  EIGHT epilogue warps: a warp may only read its own TMEM
+// lane quadrant (warp % 4), so two warps share a quadrant and take the even / odd 32-column chunks of the accumulator.
+// With one epilogue warp per scheduler every dependent instruction paid its full latency (ncu: the MMA warp spinning on
+// acc_empty, stall_wait / long_scoreboard / branch_resolving spread over the whole epilogue) and the shallow-K layers ran
+// at 2 400 cycles per chunk; two warps per scheduler overlap each other's latencies.
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int HEAD_BYTES = kMaxHead * 256 * 4;
-constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256 + HEAD_BYTES;
+constexpr int kMaxBias = 2048;   // bias of the whole layer staged in shared memory (Cout_pad <= kMaxBias)
+constexpr int kMaxRank1 = 1024;  // same for the rank-1 input column
+constexpr int HX_BYTES = 2 * BM * kMaxHead * 4;  // fused head: partial sums handed from the odd-chunk to the even-chunk warps
+constexpr int SMEM_BYTES = RING_BYTES + 256 + HEAD_BYTES + kMaxBias * 4 + kMaxRank1 * 4 + HX_BYTES;
+static_assert(SMEM_BYTES <= 232448, "conv: shared-memory budget");
 
 struct Params {
   int batch, ho, wo, cout;
@@ -221,6 +232,20 @@ __device__ __forceinline__ bool tile_decode(int u, int rank, const Params& p, in
 // hidden-state update of the sensory updaters.
 enum { EPI_PLAIN = 0, EPI_HEAD = 1, EPI_GATES = 2 };
 
+// v[j] for a run-time j without spilling v to local memory: 5-level select tree (31 selects).
+__device__ __forceinline__ float pick32(const float (&v)[32], int j) {
+  float a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? v[i + 16] : v[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[i + 8] : a[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[i + 4] : b[i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 2) ? c[i + 2] : c[i];
+  return (j & 1) ? d[1] : d[0];
+}
+
 __device__ __forceinline__ float sigmoid_fast(float x) { return 1.f / (1.f + __expf(-x)); }
 
 template <bool PAIR, int EPI>
@@ -242,6 +267,9 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_head = reinterpret_cast<float*>(smem + RING_BYTES + 256);  // [kMaxHead][256] fused-head weights
+  float* s_bias = s_head + kMaxHead * 256;                            // [kMaxBias] bias of every output channel
+  float* s_r1w = s_bias + kMaxBias;                                   // [kMaxRank1] rank-1 column
+  float* s_hx = s_r1w + kMaxRank1;                                    // [2][BM][kMaxHead] head partial sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -264,8 +292,14 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
     // empty[]: one tcgen05.commit arrive per MMA-issuing CTA that reads the stage (PAIR: the single pair MMA)
     for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], PAIR ? 1 : cs); }
     // acc_empty[]: PAIR -> the leader's barrier collects the epilogue warps of both CTAs
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 8 : 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
     fence_barrier_init();
+  }
+  {  // bias (and the rank-1 column) of the whole layer: read once per CTA instead of once per chunk from global memory
+    const int cout_pad = p.n_tiles * p.nt;
+    for (int i = threadIdx.x; i < cout_pad; i += THREADS) s_bias[i] = p.bias[i];
+    if (p.rank1_w)
+      for (int i = threadIdx.x; i < cout_pad; i += THREADS) s_r1w[i] = p.rank1_w[i];
   }
   if (warp == 1) {
     if constexpr (PAIR) tmem_alloc_2sm<512>(tmem_slot);
@@ -362,18 +396,19 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       }
     }
   } else {
-    const int quad = warp & 3;         // TMEM lane quadrant this warp may read
-    const int row = quad * 32 + lane;  // pixel within the tile
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;   // 0: even 32-column chunks, 1: odd ones
+    const int row = quad * 32 + lane;   // pixel within the tile
     const int ty = row / p.tw, tx = row - ty * p.tw;
     const bool vec_ok = (p.cout % 8) == 0;
     const bool wide = (p.cout % 16) == 0;   // 32-byte aligned channel chunks: 256-bit loads / stores
     const bool wide8 = (p.cout % 32) == 0;  // same for the 1-byte e4m3 output
     if constexpr (HEAD) {  // stage the head weights once per CTA (epilogue warps only), zero padded
-      for (int i = threadIdx.x - 64; i < kMaxHead * 256; i += 128) {
+      for (int i = threadIdx.x - 64; i < kMaxHead * 256; i += EPI_THREADS) {
         const int t = i / 256, ch = i - t * 256;
         s_head[i] = (t < p.head_n && ch < p.cout) ? p.head_w[t * p.cout + ch] : 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, EPI_THREADS);
     }
     int it = 0;
     for (int u = cluster_id; u < total_units; u += n_clusters, ++it) {
@@ -389,23 +424,24 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       const float r1x = (p.rank1_x && live) ? p.rank1_x[pix] : 0.f;
       const int acc = it & 1;
       if constexpr (EPI == EPI_GATES) {
-        // channel tile = [forget | update | new] x 64 for hidden channels hc0 .. hc0+63 (modules.py:145-149)
+        // channel tile = [forget | update | new] x 64 for hidden channels hc0 .. hc0+63 (modules.py:145-149);
+        // this warp finishes hidden channels hc0 + 32*half .. +31
         const int hc0 = (n0 / 192) * 64;
         const long long hoff = pix * p.gate_c + hc0;
+        const int c = half;
+        uint4 hv[4];
+        if (live) load_res32(p.gate_h + hoff + c * 32, hv, true);  // gate_c % 64 == 0: always 32-byte aligned
         mbar_wait(&acc_full[acc], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + acc * 256;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        {
           uint32_t rf[32], ru[32], rn[32];
           tmem_ld_32x32(t_addr + c * 32, rf);
           tmem_ld_32x32(t_addr + 64 + c * 32, ru);
           tmem_ld_32x32(t_addr + 128 + c * 32, rn);
-          uint4 hv[4];
-          if (live) load_res32(p.gate_h + hoff + c * 32, hv, true);  // gate_c % 64 == 0: always 32-byte aligned
           tmem_ld_wait();
           if (live) {
-            const float* bf = p.bias + n0 + c * 32;
+            const float* bf = s_bias + n0 + c * 32;
             uint4 ovs[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -441,27 +477,27 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
       float hacc[kMaxHead];
 #pragma unroll
       for (int t = 0; t < kMaxHead; ++t) hacc[t] = 0.f;
-      // Software pipeline over 32-channel chunks: the TMEM load and the residual loads of chunk c+1 are in flight
-      // while chunk c is finished (the residual comes from L2/HBM: ~1 us if waited for in place); the first chunk's
-      // residual is requested before the accumulator is even complete.
+      // Software pipeline over this warp's 32-channel chunks (c = half, half + 2, ...): the TMEM load and the residual
+      // loads of its next chunk are in flight while the current one is finished (the residual comes from L2/HBM: ~1 us
+      // if waited for in place); the first chunk's residual is requested before the accumulator is even complete.
       const int n_chunks = p.nt / 32;
       const float acc_scale = p.acc_scale;
       const bool res_pf = res && live && vec_ok && (p.cout % 32 == 0);
       uint32_t r[32];
       uint4 res_cur[4], res_nxt[4];
-      if (res_pf && n0 + 32 <= p.cout) load_res32(res, res_cur, wide);
+      if (res_pf && half < n_chunks && n0 + (half + 1) * 32 <= p.cout) load_res32(res + half * 32, res_cur, wide);
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + acc * 256;
-      tmem_ld_32x32(t_addr, r);
+      if (half < n_chunks) tmem_ld_32x32(t_addr + half * 32, r);
       auto chunk = [&](const int c) {
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * acc_scale;  // 1 unless the operands were pre-scaled (fp8 mode)
-        if (c + 1 < n_chunks) {
-          tmem_ld_32x32(t_addr + (c + 1) * 32, r);
-          if (res_pf && n0 + (c + 2) * 32 <= p.cout) load_res32(res + (c + 1) * 32, res_nxt, wide);
+        if (c + 2 < n_chunks) {
+          tmem_ld_32x32(t_addr + (c + 2) * 32, r);
+          if (res_pf && n0 + (c + 3) * 32 <= p.cout) load_res32(res + (c + 2) * 32, res_nxt, wide);
         }
         const int ch0 = n0 + c * 32;
         if (live && ch0 < p.cout) {
@@ -469,14 +505,14 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
             if (ks == 0) {  // partial sums of the later k-splits carry no bias
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 bv = *reinterpret_cast<const float4*>(p.bias + ch0 + j);
+                const float4 bv = *reinterpret_cast<const float4*>(s_bias + ch0 + j);
                 v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
               }
             }
             if (p.rank1_w) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 wv = *reinterpret_cast<const float4*>(p.rank1_w + ch0 + j);
+                const float4 wv = *reinterpret_cast<const float4*>(s_r1w + ch0 + j);
                 v[j] = fmaf(wv.x, r1x, v[j]); v[j + 1] = fmaf(wv.y, r1x, v[j + 1]);
                 v[j + 2] = fmaf(wv.z, r1x, v[j + 2]); v[j + 3] = fmaf(wv.w, r1x, v[j + 3]);
               }
@@ -541,28 +577,28 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
                 stg256(o32 + j, a, b);
               }
             }
-          } else {  // ragged channel tail (e.g. Cout = 1, 129): scalar path
-#pragma unroll
+          } else {  // ragged channel tail (e.g. Cout = 1, 129): scalar path, rolled (the value comes out of the
+            // register array through a select tree, so the 32 copies of this body do not sit in the instruction stream)
+#pragma unroll 1
             for (int j = 0; j < 32; ++j) {
               const int ch = ch0 + j;
-              if (ch < p.cout) {
-                float o = v[j] + (ks == 0 ? p.bias[ch] : 0.f);
-                if (p.rank1_w) o = fmaf(p.rank1_w[ch], r1x, o);
-                if (res) o += __half2float(res[c * 32 + j]);
-                if (res_lo) o += __half2float(res_lo[c * 32 + j]);
-                if (p.out_raw) {
-                  const __half hv = __float2half_rn(o);
-                  p.out_raw[off + c * 32 + j] = hv;
-                  if (p.out_raw_lo) p.out_raw_lo[off + c * 32 + j] = __float2half_rn(o - __half2float(hv));
-                }
-                if (p.out_relu) {
-                  const float ro = fmaxf(o, 0.f);
-                  const __half hv = __float2half_rn(ro);
-                  p.out_relu[off + c * 32 + j] = hv;
-                  if (p.out_relu_lo) p.out_relu_lo[off + c * 32 + j] = __float2half_rn(ro - __half2float(hv));
-                }
-                if (p.out_f32) p.out_f32[ks * p.f32_split_stride + off + c * 32 + j] = o;
+              if (ch >= p.cout) break;
+              float o = pick32(v, j) + (ks == 0 ? p.bias[ch] : 0.f);
+              if (p.rank1_w) o = fmaf(p.rank1_w[ch], r1x, o);
+              if (res) o += __half2float(res[c * 32 + j]);
+              if (res_lo) o += __half2float(res_lo[c * 32 + j]);
+              if (p.out_raw) {
+                const __half hv = __float2half_rn(o);
+                p.out_raw[off + c * 32 + j] = hv;
+                if (p.out_raw_lo) p.out_raw_lo[off + c * 32 + j] = __float2half_rn(o - __half2float(hv));
               }
+              if (p.out_relu) {
+                const float ro = fmaxf(o, 0.f);
+                const __half hv = __float2half_rn(ro);
+                p.out_relu[off + c * 32 + j] = hv;
+                if (p.out_relu_lo) p.out_relu_lo[off + c * 32 + j] = __float2half_rn(ro - __half2float(hv));
+              }
+              if (p.out_f32) p.out_f32[ks * p.f32_split_stride + off + c * 32 + j] = o;
             }
           }
         }
@@ -570,17 +606,27 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
         for (int j = 0; j < 4; ++j) res_cur[j] = res_nxt[j];
       };
 #pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) chunk(c);
+      for (int c = half; c < n_chunks; c += 2) chunk(c);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if constexpr (PAIR) mbar_arrive_cluster_relaxed(&acc_empty[acc], 0);  // tcgen05.ld are complete; no stores to publish
         else mbar_arrive(&acc_empty[acc]);
       }
-      if (HEAD && live) {
+      if constexpr (HEAD) {
+        // the two warps of a quadrant hold the head sums of the even / odd chunks of the same pixels: the odd-chunk warp
+        // hands its sums over through shared memory (double-buffered by tile, one named barrier per tile)
+        float* hx = s_hx + (it & 1) * (BM * kMaxHead) + row * kMaxHead;
+        if (half == 1) {
 #pragma unroll
-        for (int t = 0; t < kMaxHead; ++t)
-          if (t < p.head_n) p.head_out[pix * p.head_n + t] = hacc[t];
+          for (int t = 0; t < kMaxHead; ++t) hx[t] = hacc[t];
+        }
+        named_bar_sync(2, EPI_THREADS);
+        if (half == 0 && live) {
+#pragma unroll
+          for (int t = 0; t < kMaxHead; ++t)
+            if (t < p.head_n) p.head_out[pix * p.head_n + t] = hacc[t] + hx[t];
+        }
       }
       }  // plain / head epilogue
     }
@@ -605,6 +651,9 @@ int launch_conv(const ConvDesc& d, cudaStream_t stream) {
   B200_REQUIRE(d.kh == d.kw && (d.kh == 1 || d.kh == 3), "conv: %dx%d filter unsupported here", d.kh, d.kw);
   B200_REQUIRE(d.nt % 32 == 0 && d.nt >= 32 && d.nt <= 256 && d.cout_pad % d.nt == 0, "conv: bad channel tile %d", d.nt);
   B200_REQUIRE(d.tw * d.th == 128 && d.tw <= 256 && d.th <= 256, "conv: spatial tile %dx%d must cover 128 pixels", d.th, d.tw);
+  B200_REQUIRE(d.cout_pad <= conv::kMaxBias && (!d.rank1_w || d.cout_pad <= conv::kMaxRank1),
+               "conv: Cout_pad %d exceeds the shared-memory bias table (%d; %d with a rank-1 input)", d.cout_pad, conv::kMaxBias,
+               conv::kMaxRank1);
   const int pad = d.kh / 2;
   const int ho = (d.h + 2 * pad - d.kh) / d.stride + 1;
   const int wo = (d.w + 2 * pad - d.kw) / d.stride + 1;
