@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DEVA_B200_ABI_VERSION 10
+#define DEVA_B200_ABI_VERSION 11
 #define DEVA_B200_LIST_PITCH 32 /* row pitch of top-k outputs == max supported top_k */
 #define DEVA_B200_MAX_GROUPS 256 /* objects per deva_b200_readout call */
 
@@ -230,7 +230,7 @@ DEVA_B200_API int deva_b200_up2_add(const void* g, const void* skip, void* raw, 
 /* F.interpolate(mode='area') by an integer ratio r (group_modules.py:33-38), fp16 NHWC and fp32 planes */
 DEVA_B200_API int deva_b200_area_down(const void* x, void* y, int b, int h, int w, int c, int r, deva_stream_t stream);
 DEVA_B200_API int deva_b200_area_down_plane(const float* x, float* y, int b, int h, int w, int r, deva_stream_t stream);
-/* x + CBAM(x) (cbam.py:21-77 inside group_modules.py:146-150); scratch: fp32 [33*b*c + 2*b*h*w] */
+/* x + CBAM(x) (cbam.py:21-77 inside group_modules.py:146-150); scratch: fp32 [129*b*c + 2*b*h*w] (2 x 64 pooling slices + the gate, then the per-pixel statistics); c = 8 x a divisor of 256 */
 DEVA_B200_API int deva_b200_cbam(const void* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                  const float* ws, const float* bs, float* scratch, void* raw, void* relu, int b, int h,
                                  int w, int c, int r, deva_stream_t stream);

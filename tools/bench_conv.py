@@ -21,6 +21,9 @@ CASES = {
     'g16_1x1': (16, 68, 120, 512, 512, 1, 'raw'),
     'g8_1x1_res': (16, 68, 120, 256, 512, 1, 'raw+res'),
     'stem_1x1': (16, 544, 960, 64, 64, 1, 'relu'),
+    # the sensory update as the product runs it: gate epilogue, 192-column tiles; and the plain epilogue on 192-column tiles
+    'gru_gates': (16, 68, 120, 512, 1536, 3, 'gates'),
+    'gru_n192': (16, 68, 120, 512, 1536, 3, 'two192'),
 }
 
 
@@ -29,22 +32,26 @@ def run(name, iters=8):
     dev = 'cuda'
     g = torch.Generator(device=dev).manual_seed(0)
     x = torch.randn(b, h, w, cin, device=dev, generator=g).half()
-    wgt = torch.randn(cout, cin * (2 if mode == 'two' else 1), k, k, device=dev, generator=g) / (cin * k * k)**0.5
+    two = mode in ('two', 'gates', 'two192')
+    wgt = torch.randn(cout, cin * (2 if two else 1), k, k, device=dev, generator=g) / (cin * k * k)**0.5
     bias = torch.randn(cout, device=dev, generator=g)
-    pc = ops.PackedConv(wgt, bias, 1, two_inputs=(mode == 'two'), precise=(mode == 'precise'), act_lo=(mode == 'actlo'))
+    pc = ops.PackedConv(wgt, bias, 1, two_inputs=two, precise=(mode == 'precise'), act_lo=(mode == 'actlo'),
+                        gates=(mode == 'gates'), nt_override=192 if mode == 'two192' else None)
     kw = {}
-    if mode == 'two':
+    if two:
         kw['x2'] = torch.randn_like(x)
+    if mode == 'gates':
+        kw['gate_h'] = kw['x2']
     if mode in ('precise', 'actlo'):
         kw['x_lo'] = (torch.randn_like(x) * 1e-3)
     if 'res' in mode:
         kw['res'] = torch.randn(b, h, w, cout, device=dev, generator=g).half()
     if 'head' in mode:
         kw['head_w'] = torch.randn(9, cout, device=dev, generator=g)
-    want = dict(want_relu=True) if mode in ('relu', ) else dict(want_raw=True)
+    want = dict(want_relu=True) if mode in ('relu', ) else (dict() if mode == 'gates' else dict(want_raw=True))
     if mode in ('precise', 'actlo'):
         want = dict(want_relu=True, want_lo=True)
-    passes = 3 if mode == 'precise' else (2 if mode in ('two', 'actlo') else 1)
+    passes = 3 if mode == 'precise' else (2 if (two or mode == 'actlo') else 1)
     flops = 2.0 * b * h * w * cout * k * k * pc.cin_pad * passes
     for _ in range(3):
         ops.conv_ex(x, pc, **kw, **want)

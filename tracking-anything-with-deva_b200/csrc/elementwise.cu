@@ -102,61 +102,71 @@ stem_im2col_kernel(const float* __restrict__ src, __half* __restrict__ dst, __ha
   }
 }
 
-// Single-plane variant (the mask stem: C = 1, Kp = 64, no remainder output).  The generic kernel spends ~120
-// instructions of index arithmetic per 16-byte store and ran at 16 % of the HBM peak on the 16 x 1088 x 1920 mask
-// planes; here a thread owns one output pixel, reads its 49 taps from a patch staged in shared memory (even / odd input
-// columns de-interleaved so consecutive pixels read consecutive words) with compile-time tap offsets, and writes the
-// whole 128-byte im2col row with four 256-bit stores.  Same values as the generic kernel.
-constexpr int IM1_XT = 128, IM1_ROWS = 4;
+// Pixel-per-thread variant for the shapes the network uses (C = 1: mask planes, Kp = 64; C = 3: image, Kp = 192, with
+// or without the fp16 remainders).  The generic kernel spends ~120 instructions of index arithmetic per 16-byte store
+// and ran at 16-28 % of the HBM peak; here a thread owns one output pixel, reads its 49*C taps from a patch staged in
+// shared memory (even / odd input columns de-interleaved so consecutive pixels read consecutive words) with compile-time
+// tap offsets, and writes its whole im2col row with 256-bit stores.  Same values as the generic kernel.
+constexpr int IM1_XT = 128;
+template <int C, int ROWS, bool LO>
 __global__ void __launch_bounds__(IM1_XT)
-stem_im2col_c1_kernel(const float* __restrict__ src, __half* __restrict__ dst, int B, int H, int W) {
-  constexpr int PR = 2 * IM1_ROWS + 5;  // input rows under IM1_ROWS output rows
+stem_im2col_px_kernel(const float* __restrict__ src, __half* __restrict__ dst, __half* __restrict__ dst_lo, int B, int H, int W) {
+  constexpr int PR = 2 * ROWS + 5;      // input rows under ROWS output rows
   constexpr int PH = IM1_XT + 3;        // input column x_in0 + 2*i (+1) for i in [0, PH)
-  __shared__ float pe[PR][PH], po[PR][PH];
+  constexpr int KP = (49 * C + 63) / 64 * 64;
+  __shared__ float pe[C][PR][PH], po[C][PR][PH];
   const int Ho = H / 2, Wo = W / 2;
-  const int groups = (Ho + IM1_ROWS - 1) / IM1_ROWS;
-  const int b = blockIdx.y / groups, yo0 = (blockIdx.y - b * groups) * IM1_ROWS;
+  const int groups = (Ho + ROWS - 1) / ROWS;
+  const int b = blockIdx.y / groups, yo0 = (blockIdx.y - b * groups) * ROWS;
   const int xo0 = blockIdx.x * IM1_XT;
   const int x_in0 = 2 * xo0 - 3, y_in0 = 2 * yo0 - 3;
-  const float* img = src + (long long)b * H * W;
-  for (int i = threadIdx.x; i < PR * 2 * PH; i += IM1_XT) {
-    const int r = i / (2 * PH), px = i - r * (2 * PH);
+  const float* img = src + (long long)b * C * H * W;
+  for (int i = threadIdx.x; i < C * PR * 2 * PH; i += IM1_XT) {
+    const int px = i % (2 * PH), r = (i / (2 * PH)) % PR, c = i / (2 * PH * PR);
     const int y = y_in0 + r, x = x_in0 + px;
-    const float v = (y >= 0 && y < H && x >= 0 && x < W) ? img[(long long)y * W + x] : 0.f;
-    if (px & 1) po[r][px >> 1] = v;
-    else pe[r][px >> 1] = v;
+    const float v = (y >= 0 && y < H && x >= 0 && x < W) ? img[((long long)c * H + y) * W + x] : 0.f;
+    if (px & 1) po[c][r][px >> 1] = v;
+    else pe[c][r][px >> 1] = v;
   }
   __syncthreads();
   const int xl = threadIdx.x, xo = xo0 + xl;
   if (xo >= Wo) return;
 #pragma unroll 1
-  for (int rr = 0; rr < IM1_ROWS; ++rr) {
+  for (int rr = 0; rr < ROWS; ++rr) {
     const int yo = yo0 + rr;
     if (yo >= Ho) break;
-    uint4 o[8];
-    __half2* h2 = reinterpret_cast<__half2*>(o);
+    const long long out = (((long long)b * Ho + yo) * Wo + xo) * KP;
 #pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2) {
-      float v[2];
+    for (int k0 = 0; k0 < KP; k0 += 16) {  // 16 columns = one 32-byte store (and one for the remainders)
+      uint4 oh[2], ol[2];
+      __half2* h2 = reinterpret_cast<__half2*>(oh);
+      __half2* l2 = reinterpret_cast<__half2*>(ol);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int k = 2 * k2 + e;
-        if (k < 49) {
-          const int ky = k / 7, kx = k - ky * 7;
-          v[e] = (kx & 1) ? po[2 * rr + ky][xl + (kx >> 1)] : pe[2 * rr + ky][xl + (kx >> 1)];
-        } else {
-          v[e] = 0.f;
+      for (int k2 = 0; k2 < 8; ++k2) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = k0 + 2 * k2 + e;  // column k = (ky*7 + kx)*C + c
+          if (k < 49 * C) {
+            const int tap = k / C, c = k - tap * C, ky = tap / 7, kx = tap - ky * 7;
+            v[e] = (kx & 1) ? po[c][2 * rr + ky][xl + (kx >> 1)] : pe[c][2 * rr + ky][xl + (kx >> 1)];
+          } else {
+            v[e] = 0.f;
+          }
+        }
+        h2[k2] = __floats2half2_rn(v[0], v[1]);
+        if (LO) {
+          const float2 back = __half22float2(h2[k2]);
+          l2[k2] = __floats2half2_rn(v[0] - back.x, v[1] - back.y);
         }
       }
-      h2[k2] = __floats2half2_rn(v[0], v[1]);
-    }
-    __half* out = dst + (((long long)b * Ho + yo) * Wo + xo) * 64;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out + 16 * j), "r"(o[2 * j].x),
-                   "r"(o[2 * j].y), "r"(o[2 * j].z), "r"(o[2 * j].w), "r"(o[2 * j + 1].x), "r"(o[2 * j + 1].y),
-                   "r"(o[2 * j + 1].z), "r"(o[2 * j + 1].w)
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + out + k0), "r"(oh[0].x), "r"(oh[0].y),
+                   "r"(oh[0].z), "r"(oh[0].w), "r"(oh[1].x), "r"(oh[1].y), "r"(oh[1].z), "r"(oh[1].w)
                    : "memory");
+      if (LO)
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst_lo + out + k0), "r"(ol[0].x),
+                     "r"(ol[0].y), "r"(ol[0].z), "r"(ol[0].w), "r"(ol[1].x), "r"(ol[1].y), "r"(ol[1].z), "r"(ol[1].w)
+                     : "memory");
     }
   }
 }
@@ -259,96 +269,84 @@ __device__ __forceinline__ void st8_split(__half* hi, __half* lo, const float (&
   *reinterpret_cast<uint4*>(hi) = vh;
   *reinterpret_cast<uint4*>(lo) = vl;
 }
-constexpr int kUpRows = 8;  // output rows walked by one thread: 8 output rows touch 5 source rows, each loaded once
 __global__ void __launch_bounds__(256)
 up2_add_split_kernel(const __half* __restrict__ g, const __half* __restrict__ g_lo, const __half* __restrict__ skip,
                      const __half* __restrict__ skip_lo, __half* __restrict__ raw, __half* __restrict__ raw_lo,
                      __half* __restrict__ relu, __half* __restrict__ relu_lo, unsigned char* __restrict__ relu_lo8, int B,
                      int h, int w, int C) {
-  // blockIdx.y = (image, group of kUpRows output rows).  A thread owns one output column X and 8 channels and walks down
-  // the rows of its group keeping the two source rows it interpolates between (at x0 and x1, hi + lo already summed) in
-  // registers: consecutive output rows share source rows, so each source row is fetched once per group instead of once
-  // per output row (the per-row version re-read the source 5x from DRAM: profiles/r02_ncu_full.md).
+  // A thread owns 8 channels of the 2 x 2 OUTPUT block {2k-1, 2k} x {2j-1, 2j}: with align_corners = False these four
+  // pixels interpolate between the same four source pixels (rows k-1, k / columns j-1, j, clamped at the border) with
+  // weights 0.25 / 0.75, so the source quad (hi + lo) is loaded once per four outputs and there is no serial walk:
+  // every thread is one independent load -> compute -> store chain (the row-walking version kept the DRAM traffic at the
+  // algorithmic 1x but ran at half the HBM rate: eight dependent rows per thread; the per-pixel version before it re-read
+  // the source 5x).  blockIdx.y = (image, k), k in [0, h]; the clamped border blocks produce the reference's values
+  // exactly (a + (a - a) * wx == a).
   const int H = 2 * h, W = 2 * w, C8 = C / 8;
-  const int groups = (H + kUpRows - 1) / kUpRows;
-  const int b = blockIdx.y / groups, Y0 = (blockIdx.y - b * groups) * kUpRows;
-  const int row_vecs = W * C8;
+  const int b = blockIdx.y / (h + 1), k = blockIdx.y - b * (h + 1);
+  const int ya = max(k - 1, 0), yb = min(k, h - 1);
+  const int row_vecs = (w + 1) * C8;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < row_vecs; i += gridDim.x * 256) {
-    const int X = i / C8, c = (i - X * C8) * 8;
-    const float sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.f);  // align_corners=False: src = (dst + 0.5)/2 - 0.5, clamped
-    const int x0 = (int)sx, x1 = min(x0 + 1, w - 1);
-    const float wx = sx - x0;
-    float r0a[8], r0b[8], r1a[8], r1b[8], l[8];  // source rows (ya, yb) at columns x0 (a) and x1 (b)
-    int ya = -1, yb = -1;
-    auto load_row = [&](const int y, float (&pa)[8], float (&pb)[8]) {
-      const long long o = (((long long)b * h + y) * w) * C + c;
-      ld8(g + o + (long long)x0 * C, pa);
-      ld8(g_lo + o + (long long)x0 * C, l);
+    const int j = i / C8, c = (i - j * C8) * 8;
+    const int xa = max(j - 1, 0), xb = min(j, w - 1);
+    float qa[8], qb[8], qc[8], qd[8], l[8];  // source quad: (ya, xa), (ya, xb), (yb, xa), (yb, xb)
+    const long long oa = (((long long)b * h + ya) * w) * C + c, ob = (((long long)b * h + yb) * w) * C + c;
+    auto load = [&](const long long o, float (&q)[8]) {
+      ld8(g + o, q);
+      ld8(g_lo + o, l);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) pa[e] += l[e];
-      ld8(g + o + (long long)x1 * C, pb);
-      ld8(g_lo + o + (long long)x1 * C, l);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) pb[e] += l[e];
+      for (int e = 0; e < 8; ++e) q[e] += l[e];
     };
-    for (int Y = Y0; Y < min(H, Y0 + kUpRows); ++Y) {
-      const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.f);
-      const int y0 = (int)sy, y1 = min(y0 + 1, h - 1);
-      const float wy = sy - y0;
-      if (y0 != ya) {
-        if (y0 == yb) {  // the lower row of the previous output row becomes the upper one
+    load(oa + (long long)xa * C, qa);
+    load(oa + (long long)xb * C, qb);
+    load(ob + (long long)xa * C, qc);
+    load(ob + (long long)xb * C, qd);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { r0a[e] = r1a[e]; r0b[e] = r1b[e]; }
-        } else {
-          load_row(y0, r0a, r0b);
+    for (int dy = 0; dy < 2; ++dy) {
+      const int Y = 2 * k - 1 + dy;
+      if (Y < 0 || Y >= H) continue;
+      const float wy = dy ? 0.75f : 0.25f;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int X = 2 * j - 1 + dx;
+        if (X < 0 || X >= W) continue;
+        const float wx = dx ? 0.75f : 0.25f;
+        float o[8], s_[8];
+        ld8(skip + ((long long)Y * W + X) * C + c, s_);
+        if (skip_lo) {
+          ld8(skip_lo + ((long long)Y * W + X) * C + c, l);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) s_[e] += l[e];
         }
-        ya = y0;
-      }
-      if (y1 != yb) {
-        if (y1 == ya) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { r1a[e] = r0a[e]; r1b[e] = r0b[e]; }
-        } else {
-          load_row(y1, r1a, r1b);
+        for (int e = 0; e < 8; ++e) {
+          const float top = qa[e] + (qb[e] - qa[e]) * wx, bot = qc[e] + (qd[e] - qc[e]) * wx;
+          o[e] = top + (bot - top) * wy + s_[e];
         }
-        yb = y1;
-      }
-      float o[8], s_[8];
-      ld8(skip + ((long long)Y * W + X) * C + c, s_);
-      if (skip_lo) {
-        ld8(skip_lo + ((long long)Y * W + X) * C + c, l);
+        const long long off = (((long long)b * H + Y) * W + X) * C + c;
+        if (raw) st8_split(raw + off, raw_lo + off, o);
+        if (relu_lo) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) s_[e] += l[e];
-      }
+          for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+          st8_split(relu + off, relu_lo + off, o);
+        } else if (relu_lo8) {  // low-order part as e4m3 of (x - fp16(x)) * 4096: operand of an fp8 correction pass
+          uint32_t w8[2];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float top = r0a[e] + (r0b[e] - r0a[e]) * wx, bot = r1a[e] + (r1b[e] - r1a[e]) * wx;
-        o[e] = top + (bot - top) * wy + s_[e];
-      }
-      const long long off = (((long long)b * H + Y) * W + X) * C + c;
-      if (raw) st8_split(raw + off, raw_lo + off, o);
-      if (relu_lo) {
+          for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+          st8(relu + off, o, false);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
-        st8_split(relu + off, relu_lo + off, o);
-      } else if (relu_lo8) {  // low-order part as e4m3 of (x - fp16(x)) * 4096: operand of an fp8 correction pass
-        uint32_t w8[2];
+          for (int e = 0; e < 2; ++e) {
+            float q4[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
-        st8(relu + off, o, false);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          float q4[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) q4[t] = (o[4 * e + t] - __half2float(__float2half_rn(o[4 * e + t]))) * 4096.f;
-          unsigned short a16, b16;
-          asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(a16) : "f"(q4[1]), "f"(q4[0]));
-          asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(b16) : "f"(q4[3]), "f"(q4[2]));
-          w8[e] = (uint32_t)a16 | ((uint32_t)b16 << 16);
+            for (int t = 0; t < 4; ++t) q4[t] = (o[4 * e + t] - __half2float(__float2half_rn(o[4 * e + t]))) * 4096.f;
+            unsigned short a16, b16;
+            asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(a16) : "f"(q4[1]), "f"(q4[0]));
+            asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(b16) : "f"(q4[3]), "f"(q4[2]));
+            w8[e] = (uint32_t)a16 | ((uint32_t)b16 << 16);
+          }
+          *reinterpret_cast<uint2*>(relu_lo8 + off) = make_uint2(w8[0], w8[1]);
+        } else if (relu) {
+          st8(relu + off, o, true);
         }
-        *reinterpret_cast<uint2*>(relu_lo8 + off) = make_uint2(w8[0], w8[1]);
-      } else if (relu) {
-        st8(relu + off, o, true);
       }
     }
   }
@@ -396,25 +394,50 @@ __global__ void area_down_plane_kernel(const float* __restrict__ x, float* __res
 }
 
 // ---------------------------------------------------------------- CBAM (cbam.py:21-77)
-// per (image, channel) partial sum and max over a slice of the pixels: grid (C/128, B, kPoolSplit)
-constexpr int kPoolSplit = 16;
-__global__ void cbam_pool_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, float* __restrict__ psum,
-                                 float* __restrict__ pmax, int HW, int C) {
-  const int b = blockIdx.y, sp = blockIdx.z;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// per (image, channel) partial sum and max over a slice of the pixels.  grid (B, kPoolSplit), 256 threads: a thread owns
+// 8 channels (one 16-byte load per pixel and operand) and every (256 / (C/8))-th pixel of the slice; the pixel lanes are
+// folded through shared memory.  (The one-channel-per-thread version issued 2-byte loads: 64 bytes per warp instruction.)
+constexpr int kPoolSplit = 64;
+__global__ void __launch_bounds__(256)
+cbam_pool_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, float* __restrict__ psum,
+                 float* __restrict__ pmax, int HW, int C) {
+  __shared__ float ss[256 * 8], sm[256 * 8];
+  const int b = blockIdx.x, sp = blockIdx.y;
+  const int C8 = C / 8, lanes = 256 / C8;  // pixel lanes (host guarantees 256 % C8 == 0)
+  const int cv = threadIdx.x % C8, pl = threadIdx.x / C8;
   const int per = (HW + kPoolSplit - 1) / kPoolSplit;
   const int i0 = sp * per, i1 = min(HW, i0 + per);
-  const __half* p = x + (long long)b * HW * C + c;
-  const __half* pl = x_lo ? x_lo + (long long)b * HW * C + c : nullptr;
-  float s = 0.f, m = -CUDART_INF_F;
-  for (int i = i0; i < i1; ++i) {
-    const float v = __half2float(p[(long long)i * C]) + (pl ? __half2float(pl[(long long)i * C]) : 0.f);
-    s += v;
-    m = fmaxf(m, v);
+  float s[8], m[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s[e] = 0.f; m[e] = -CUDART_INF_F; }
+  for (int i = i0 + pl; i < i1; i += lanes) {
+    const long long o = ((long long)b * HW + i) * C + cv * 8;
+    float v[8];
+    ld8(x + o, v);
+    if (x_lo) {
+      float l[8];
+      ld8(x_lo + o, l);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += l[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] += v[e]; m[e] = fmaxf(m[e], v[e]); }
   }
-  psum[((long long)b * kPoolSplit + sp) * C + c] = s;
-  pmax[((long long)b * kPoolSplit + sp) * C + c] = m;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { ss[e * 256 + threadIdx.x] = s[e]; sm[e * 256 + threadIdx.x] = m[e]; }
+  __syncthreads();
+  if (pl == 0) {
+    for (int q = 1; q < lanes; ++q) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s[e] += ss[e * 256 + q * C8 + cv];
+        m[e] = fmaxf(m[e], sm[e * 256 + q * C8 + cv]);
+      }
+    }
+    const long long o = ((long long)b * kPoolSplit + sp) * C + cv * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { psum[o + e] = s[e]; pmax[o + e] = m[e]; }
+  }
 }
 // gate[b,c] = sigmoid(mlp(avg) + mlp(max)), mlp = Linear(C,R) -> ReLU -> Linear(R,C); one block per image
 __global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int HW,
@@ -451,7 +474,7 @@ __global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __r
     gate[b * C + c] = sigmoidf_(a);
   }
 }
-// per pixel: max and mean over channels of x * gate -> stats [B,HW,2]; one warp per pixel
+// per pixel: max and mean over channels of x * gate -> stats [B,HW,2]; one warp per pixel, 8 channels per lane and load
 __global__ void cbam_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo, const float* __restrict__ gate,
                                   float* __restrict__ stats, int B, int HW, int C) {
   const long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -462,10 +485,23 @@ __global__ void cbam_stats_kernel(const __half* __restrict__ x, const __half* __
   const __half* pl = x_lo ? x_lo + pix * C : nullptr;
   const float* g = gate + b * C;
   float s = 0.f, m = -CUDART_INF_F;
-  for (int c = lane; c < C; c += 32) {
-    const float v = (__half2float(p[c]) + (pl ? __half2float(pl[c]) : 0.f)) * g[c];
-    s += v;
-    m = fmaxf(m, v);
+  for (int c = lane * 8; c < C; c += 256) {
+    float v[8];
+    ld8(p + c, v);
+    if (pl) {
+      float l[8];
+      ld8(pl + c, l);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += l[e];
+    }
+    const float4 g0 = *reinterpret_cast<const float4*>(g + c), g1 = *reinterpret_cast<const float4*>(g + c + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float t = v[e] * gg[e];
+      s += t;
+      m = fmaxf(m, t);
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -492,11 +528,13 @@ __global__ void cbam_apply_kernel(const __half* __restrict__ x, const float* __r
   for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
   const float sg = sigmoidf_(a + bs[0]);
   const float* g = gate + b * C;
-  for (int c = lane; c < C; c += 32) {
-    const float v = __half2float(x[pix * C + c]);
-    const float o = v + v * g[c] * sg;
-    if (raw) raw[pix * C + c] = __float2half_rn(o);
-    if (relu) relu[pix * C + c] = __float2half_rn(fmaxf(o, 0.f));
+  for (int c = lane * 8; c < C; c += 256) {
+    float v[8], o[8];
+    ld8(x + pix * C + c, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = v[e] + v[e] * g[c + e] * sg;
+    if (raw) st8(raw + pix * C + c, o, false);
+    if (relu) st8(relu + pix * C + c, o, true);
   }
 }
 
@@ -521,17 +559,21 @@ __global__ void cbam_apply_split_kernel(const __half* __restrict__ x, const __ha
   for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
   const float sg = sigmoidf_(a + bs[0]);
   const float* g = gate + b * C;
-  for (int c = lane; c < C; c += 32) {
-    const float v = __half2float(x[pix * C + c]) + __half2float(x_lo[pix * C + c]);
-    const float o = v + v * g[c] * sg;
-    const __half hi = __float2half_rn(o);
-    raw[pix * C + c] = hi;
-    raw_lo[pix * C + c] = __float2half_rn(o - __half2float(hi));
+  for (int c = lane * 8; c < C; c += 256) {
+    float v[8], l[8], o[8];
+    ld8(x + pix * C + c, v);
+    ld8(x_lo + pix * C + c, l);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float t = v[e] + l[e];
+      o[e] = t + t * g[c + e] * sg;
+    }
+    st8_split(raw + pix * C + c, raw_lo + pix * C + c, o);
     if (relu) {
-      const float ro = fmaxf(o, 0.f);
-      const __half rh = __float2half_rn(ro);
-      relu[pix * C + c] = rh;
-      if (relu_lo) relu_lo[pix * C + c] = __float2half_rn(ro - __half2float(rh));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+      if (relu_lo) st8_split(relu + pix * C + c, relu_lo + pix * C + c, o);
+      else st8(relu + pix * C + c, o, false);
     }
   }
 }
@@ -727,9 +769,16 @@ int ew_stem_im2col(const float* src, __half* dst, __half* dst_lo, int B, int C, 
   B200_REQUIRE(H % 2 == 0 && W % 2 == 0 && Kp % 64 == 0 && Kp >= 49 * C, "stem_im2col: bad shape");
   B200_REQUIRE(C >= 1 && C <= 8, "stem_im2col: at most 8 input planes");
   const size_t smem = (size_t)C * 7 * (2 * ew::IM_XT + 5) * sizeof(float);
-  if (C == 1 && Kp == 64 && !dst_lo) {  // mask planes: one thread per output pixel, 128-byte rows
-    ew::stem_im2col_c1_kernel<<<dim3(ceil_div(W / 2, ew::IM1_XT), B * ceil_div(H / 2, ew::IM1_ROWS)), ew::IM1_XT, 0, s>>>(
-        src, dst, B, H, W);
+  // the network's shapes: one thread per output pixel, whole im2col rows written with 256-bit stores
+  const dim3 gx(ceil_div(W / 2, ew::IM1_XT));
+  if (C == 1 && Kp == 64 && !dst_lo) {
+    ew::stem_im2col_px_kernel<1, 4, false><<<dim3(gx.x, B * ceil_div(H / 2, 4)), ew::IM1_XT, 0, s>>>(src, dst, nullptr, B, H, W);
+    B200_LAUNCH_CHECK();
+    return 0;
+  }
+  if (C == 3 && Kp == 192) {
+    if (dst_lo) ew::stem_im2col_px_kernel<3, 2, true><<<dim3(gx.x, B * ceil_div(H / 2, 2)), ew::IM1_XT, 0, s>>>(src, dst, dst_lo, B, H, W);
+    else ew::stem_im2col_px_kernel<3, 2, false><<<dim3(gx.x, B * ceil_div(H / 2, 2)), ew::IM1_XT, 0, s>>>(src, dst, nullptr, B, H, W);
     B200_LAUNCH_CHECK();
     return 0;
   }
@@ -755,7 +804,7 @@ int ew_up2_add_split(const __half* g, const __half* g_lo, const __half* skip, co
   B200_REQUIRE(C % 8 == 0 && g_lo && (raw != nullptr) == (raw_lo != nullptr) && (raw || relu) && (!relu_lo || relu) &&
                    (!relu_lo8 || (relu && !relu_lo)),
                "up2_add_split: C %% 8, g_lo, and raw/raw_lo (both or neither) with at least one output are required");
-  ew::up2_add_split_kernel<<<dim3(ceil_div(2 * w * (C / 8), 256), B * ceil_div(2 * h, ew::kUpRows)), 256, 0, s>>>(
+  ew::up2_add_split_kernel<<<dim3(ceil_div((w + 1) * (C / 8), 256), B * (h + 1)), 256, 0, s>>>(
       g, g_lo, skip, skip_lo, raw, raw_lo, relu, relu_lo, relu_lo8, B, h, w, C);
   B200_LAUNCH_CHECK();
   return 0;
@@ -782,7 +831,8 @@ int ew_cbam(const __half* x, const float* w1, const float* b1, const float* w2, 
   float* gate = pmax + (long long)B * ew::kPoolSplit * C;
   float* stats = gate + (long long)B * C;
   const int HW = H * W;
-  ew::cbam_pool_kernel<<<dim3(ceil_div(C, 128), B, ew::kPoolSplit), 128, 0, s>>>(x, nullptr, psum, pmax, HW, C);
+  B200_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "cbam: C = %d must be 8 x a divisor of 256", C);
+  ew::cbam_pool_kernel<<<dim3(B, ew::kPoolSplit), 256, 0, s>>>(x, nullptr, psum, pmax, HW, C);
   B200_LAUNCH_CHECK();
   ew::cbam_mlp_kernel<<<B, 256, (2 * C + 2 * R) * sizeof(float), s>>>(psum, pmax, HW, w1, b1, w2, b2, gate, C, R);
   B200_LAUNCH_CHECK();
@@ -804,7 +854,8 @@ int ew_cbam_split(const __half* x, const __half* x_lo, const float* w1, const fl
   float* gate = pmax + (long long)B * ew::kPoolSplit * C;
   float* stats = gate + (long long)B * C;
   const int HW = H * W;
-  ew::cbam_pool_kernel<<<dim3(ceil_div(C, 128), B, ew::kPoolSplit), 128, 0, s>>>(x, pool_lo ? x_lo : nullptr, psum, pmax, HW, C);
+  B200_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "cbam_split: C = %d must be 8 x a divisor of 256", C);
+  ew::cbam_pool_kernel<<<dim3(B, ew::kPoolSplit), 256, 0, s>>>(x, pool_lo ? x_lo : nullptr, psum, pmax, HW, C);
   B200_LAUNCH_CHECK();
   ew::cbam_mlp_kernel<<<B, 256, (2 * C + 2 * R) * sizeof(float), s>>>(psum, pmax, HW, w1, b1, w2, b2, gate, C, R);
   B200_LAUNCH_CHECK();

@@ -10,6 +10,7 @@ import torch
 
 from deva import _native as nat
 
+CBAM_POOL_SPLIT = 64  # csrc/elementwise.cu kPoolSplit: pixel slices of the CBAM channel pooling (scratch layout)
 MAX_CHAIN = 32  # longest single accumulation chain of a split-precision conv (k-iterations of 64 channels)
 CHAIN = 27      # chain length when a longer loop is split (= one 3x3 filter over 64 channels in three passes)
 PROFILE = None  # set to a list by bench.py to collect (start event, end event, algorithmic FLOPs, MMA passes) per conv
@@ -35,7 +36,8 @@ class PackedConv:
     """One convolution ready for ``deva_b200_conv2d``."""
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int,
                  rank1_in: Optional[int] = None, two_inputs: bool = False, precise: bool = False,
-                 gates: bool = False, act_lo: bool = False, w_lo: bool = False, act_lo8: bool = False):
+                 gates: bool = False, act_lo: bool = False, w_lo: bool = False, act_lo8: bool = False,
+                 nt_override: Optional[int] = None):
         """weight [Cout, Cin, k, k] fp32 (BN folded); if ``rank1_in`` is given, that input channel is split
         off as a rank-1 term (out += w[:, rank1_in] * x1) - used for the '+1' mask / logit channels.
         ``gates``: Cout = [forget | update | new] x C of a sensory updater; rows are regrouped so that every
@@ -84,6 +86,9 @@ class PackedConv:
             self.nt = _round_up(cout, 32)
         if self.nt == 0:
             self.nt = 256
+        if nt_override is not None:  # channel-tile experiments (tools/bench_conv.py)
+            assert not gates and nt_override % 32 == 0 and 32 <= nt_override <= 256
+            self.nt = nt_override
         self.cout_pad = _round_up(cout, self.nt)
         nsrc = 2 if two_inputs else 1
         w = torch.zeros(self.cout_pad, nsrc, kh * kw, self.cin_pad, dtype=torch.float32, device=dev)
@@ -302,7 +307,7 @@ def cbam_residual(x: torch.Tensor, params: dict, want_raw=True, want_relu=True):
     """x + CBAM(x) on fp16 NHWC; params: w1,b1,w2,b2 (channel MLP), ws [2*49], bs [1] (fp32)."""
     b, h, w, c = x.shape
     r = params['w1'].shape[0]
-    scratch = torch.empty(33 * b * c + 2 * b * h * w, dtype=torch.float32, device=x.device)
+    scratch = torch.empty((2 * CBAM_POOL_SPLIT + 1) * b * c + 2 * b * h * w, dtype=torch.float32, device=x.device)
     raw = torch.empty_like(x) if want_raw else None
     relu = torch.empty_like(x) if want_relu else None
     nat.cbam(x, params['w1'], params['b1'], params['w2'], params['b2'], params['ws'], params['bs'], scratch, raw, relu,
@@ -317,7 +322,7 @@ def cbam_residual_split(x: torch.Tensor, x_lo: torch.Tensor, params: dict, want_
     """(x + x_lo) + CBAM(x + x_lo) -> (raw, raw_lo, relu, relu_lo)."""
     b, h, w, c = x.shape
     r = params['w1'].shape[0]
-    scratch = torch.empty(33 * b * c + 2 * b * h * w, dtype=torch.float32, device=x.device)
+    scratch = torch.empty((2 * CBAM_POOL_SPLIT + 1) * b * c + 2 * b * h * w, dtype=torch.float32, device=x.device)
     raw, raw_lo, relu = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
     relu_lo = torch.empty_like(x) if want_relu_lo else None
     nat.cbam_split(x, x_lo, params['w1'], params['b1'], params['w2'], params['b2'], params['ws'], params['bs'], scratch,
