@@ -205,6 +205,25 @@ def test_stem_matches_torch(k_obj, h, w):
     assert float((_nchw(out) - ref).abs().max()) < 1e-2
 
 
+@pytest.mark.parametrize('c,h,w,with_lo', [(1, 44, 520, False), (3, 44, 520, True), (3, 32, 48, False), (2, 20, 36, True)])
+def test_stem_columns_exact(c, h, w, with_lo):
+    """im2col of the 7x7 stride-2 pad-3 stems: column (ky*7 + kx)*C + c, fp16 value and fp16 remainder, zero padded -
+    bit-exact against F.unfold for the pixel-per-thread kernels (C = 1, 3) and the generic one (C = 2)."""
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(5)
+    x = torch.randn(2, c, h, w, device='cuda', generator=g)
+    kp = (49 * c + 63) // 64 * 64
+    got = ops.stem_columns(x, kp, with_lo=with_lo)
+    cols = F.unfold(x, 7, padding=3, stride=2).view(2, c, 49, h // 2, w // 2)   # [B, c, tap, Ho, Wo]
+    ref = torch.zeros(2, h // 2, w // 2, kp, device='cuda')
+    ref[..., :49 * c] = cols.permute(0, 3, 4, 2, 1).reshape(2, h // 2, w // 2, 49 * c)
+    hi = got[0] if with_lo else got
+    torch.cuda.synchronize()
+    assert torch.equal(hi, ref.half())
+    if with_lo:
+        assert torch.equal(got[1], (ref - ref.half().float()).half())
+
+
 def test_helpers_match_torch():
     ops = _ops()
     from deva import _native as nat

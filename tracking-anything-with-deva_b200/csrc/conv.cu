@@ -246,7 +246,12 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
   return (j & 1) ? d[1] : d[0];
 }
 
-__device__ __forceinline__ float sigmoid_fast(float x) { return 1.f / (1.f + __expf(-x)); }
+// Gate non-linearities of the fused hidden-state update.  ex2.approx + rcp.approx: absolute error < 1e-6 (the state is
+// stored in fp16, 5e-4), ~6 instructions each instead of ~15 (IEEE division) / ~40 (tanhf with its branchy slow path) -
+// the gate epilogue was costing the sensory update 0.4 ms per frame on top of its 192-column tiles
+// (tools/bench_conv.py gru_n192 vs gru_gates).  exp overflow -> +inf -> quotient 0 -> the correct limits 0 / 1 / -1.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 template <bool PAIR, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -457,7 +462,7 @@ conv_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params p)
                 for (int s = 0; s < 2; ++s) {
                   const float f = sigmoid_fast(__uint_as_float(rf[ch + s]) + bf[ch + s]);
                   const float u = sigmoid_fast(__uint_as_float(ru[ch + s]) + bf[64 + ch + s]);
-                  const float n = tanhf(__uint_as_float(rn[ch + s]) + bf[128 + ch + s]);
+                  const float n = tanh_fast(__uint_as_float(rn[ch + s]) + bf[128 + ch + s]);
                   o[s] = f * (s ? hp.y : hp.x) * (1.f - u) + u * n;
                 }
                 o2[e] = __floats2half2_rn(o[0], o[1]);

@@ -694,6 +694,33 @@ __global__ void up4_softmax_kernel(const float* __restrict__ agg, float* __restr
   const float wy = sy - y0, wx = sx - x0;
   const long long o00 = (long long)y0 * w + x0, o01 = (long long)y0 * w + x1, o10 = (long long)y1 * w + x0,
                   o11 = (long long)y1 * w + x1;
+  if (K1 <= 32) {  // the usual case: the K+1 interpolated logits stay in registers, prob is written once
+    float v[32];
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (k < K1) {
+        const float* a = agg + (long long)k * h * w;
+        const float top = a[o00] + (a[o01] - a[o00]) * wx, bot = a[o10] + (a[o11] - a[o10]) * wx;
+        v[k] = top + (bot - top) * wy;
+        if (logits_out) logits_out[(long long)k * H * W + i] = v[k];
+        m = fmaxf(m, v[k]);
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (k < K1) {
+        v[k] = expf(v[k] - m);
+        s += v[k];
+      }
+    }
+    const float inv = 1.f / s;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (k < K1) prob[(long long)k * H * W + i] = v[k] * inv;
+    return;
+  }
   float m = -CUDART_INF_F;
   for (int k = 0; k < K1; ++k) {
     const float* a = agg + (long long)k * h * w;
