@@ -95,10 +95,17 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={gpu_index}', f'--query-gpu={self.QUERY}',
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples written so far (start-up, warm-up) are dropped by stop()."""
+        try:
+            self.skip = sum(1 for _ in open(self.path))
+        except Exception:
+            self.skip = 0
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
@@ -111,7 +118,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         try:
-            for line in open(self.path):
+            for n_line, line in enumerate(open(self.path)):
+                if n_line < getattr(self, 'skip', 0):
+                    continue
                 f = [x.strip() for x in line.split(',')]
                 if len(f) < 9:
                     continue
@@ -245,19 +254,30 @@ class ClipSet:
             c.step_e2e_fused_io()
 
 
+HOST_MS = []  # host time (enqueue only, no sync) of every timed step of the last timed() call: a stall of the launching
+              # thread (GC, scheduler, allocator) longer than the GPU's queued work shows up in the event time as well
+
+
 def timed(fn, steps, dist_on):
+    import gc
     import torch.distributed as dist
     if dist_on:
         dist.barrier()
     torch.cuda.synchronize()
+    gc.collect()
+    gc.disable()  # no collector pause between two launches of the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    del HOST_MS[:]
     t0 = time.perf_counter()
     e0.record()
     for _ in range(steps):
+        h0 = time.perf_counter()
         fn()
+        HOST_MS.append((time.perf_counter() - h0) * 1e3)
     e1.record()
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) * 1e3
+    gc.enable()
     ms = max(e0.elapsed_time(e1), 0.0)
     if dist_on:
         t = torch.tensor([ms, wall], device='cuda')
@@ -307,11 +327,15 @@ def run_ours(args):
         clip = Clip(wl, device, seed=100 + rank)
         frames_per_step, scaling, n_clips_rank = world, 'weak', 1
     nat = clip.nat
-    for _ in range(max(args.warmup, 3)):
+    # the clock sampler starts BEFORE the warm-up: nvidia-smi's start-up (NVML initialisation takes driver locks) must not
+    # fall into the timed region; only samples taken during the timed region are kept (ClockSampler.mark)
+    sampler = ClockSampler(local) if rank == 0 else None
+    n_warm = max(args.warmup, 6)  # >= one full mem_every period: the timed region sees no first-time allocation / kernel load
+    for _ in range(n_warm):
         clip.step_resident()
     torch.cuda.synchronize()
-
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     clip.core.memory.read_events = []
     l0 = nat.launch_count()
     ms, wall = timed(clip.step_resident, args.steps, dist_on)
@@ -320,6 +344,7 @@ def run_ours(args):
     clip.core.memory.read_events = None
     read_ms = sum(a.elapsed_time(b) for a, b in ev) / max(len(ev), 1)
     clocks = sampler.stop() if sampler else None
+    host_ms = sorted(HOST_MS)
 
     for _ in range(2):
         clip.step_e2e()
@@ -379,7 +404,7 @@ def run_ours(args):
         d2h = int(wl['h'] * wl['w'])
         out = {
             'metric': METRIC, 'value': frames_per_step * args.steps / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+            'steps': args.steps, 'warmup': n_warm, 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f16 MMA operands / f32 accumulate '
             f'(tcgen05 memory read + conv stack), precision plan {precision!r}; key path split-f16x3 (~f32)', 'data': 'synthetic',
             'config': workload_config(wl, clip.q, world),
@@ -397,6 +422,7 @@ def run_ours(args):
                              'd2h_bytes_per_step': d2h * n_clips_rank,
                              'what': 'uint8 frame upload + on-device normalise; fused argmax + id remap (deva.inference.frame_io)'},
             'gpu_launches': int(launches), 'wall_ms_per_step': wall / args.steps, 'clocks': clocks,
+            'host_enqueue_ms_per_step': {'median': host_ms[len(host_ms) // 2], 'max': host_ms[-1]} if host_ms else None,
             'precision_plan': precision,
         }
     # everything below runs without the clip: give the legs the device
