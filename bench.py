@@ -439,8 +439,9 @@ def run_ours(args):
                 k: c5.get(k) for k in ('value', 'unit', 'n_gpus', 'steps', 'ms_per_step', 'scaling', 'config', 'roofline', 'e2e',
                                        'gpu_launches', 'precision_plan')}
         if world == 1 and not args.no_cpu_baseline:
-            try:  # bounded sample: 1 warm-up + 2 timed sample steps of the unmodified reference on the host cores
-                leg = _run_leg(['--impl', 'reference', '--steps', '2', '--warmup', '1', '--workload', args.workload,
+            try:  # bounded sample: 1 warm-up + 5 timed sample steps (exactly one memory frame: the right 1-in-5 weight)
+                # of the unmodified reference on the host cores; reference_cpu shortens it on a slow box and says so
+                leg = _run_leg(['--impl', 'reference', '--steps', '5', '--warmup', '1', '--workload', args.workload,
                                 '--ref-objects', str(args.ref_objects)], timeout=900)
                 out['cpu_baseline'] = leg['cpu_baseline']
             except Exception as exc:
@@ -626,7 +627,7 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def reference_cpu(wl, steps, warmup, n_obj):
+def reference_cpu(wl, steps, warmup, n_obj, budget_s=240.0):
     """The reference's own step() on the host cores.  A step of the sample is one full-resolution frame of the named
     workload with ``n_obj`` of its K objects; every per-object stage of DEVA is independent across objects (the
     reference's own note, docs/DEMO.md:41: run time is linear in the number of objects), so the full-frame time is
@@ -639,12 +640,22 @@ def reference_cpu(wl, steps, warmup, n_obj):
     t_build = time.perf_counter()
     clip = RefClip(wl, 'cpu', n_obj, seed=100)
     t_build = time.perf_counter() - t_build
+    t_warm = 0.0
     for _ in range(warmup):
+        t0 = time.perf_counter()
         clip.step()
+        t_warm = time.perf_counter() - t0
+    # time budget of the timed region (a sample step is 4 s on a fast 64-core box, 30 s on a slow 128-core one): never fewer
+    # than 2 steps, never more than requested; a shortened run is flagged and the value stays a per-step average
+    requested = steps
+    if t_warm > 0 and steps * t_warm > budget_s:
+        steps = max(2, min(steps, int(budget_s / t_warm)))
     timer = _SharedTimer(clip.net)
+    mem_frames = 0
     t0 = time.perf_counter()
     for _ in range(steps):
         clip.step()
+        mem_frames += int(clip.core.last_mem_ti == clip.core.curr_ti)
     wall = time.perf_counter() - t0
     timer.close()
     t_step = wall / steps
@@ -652,7 +663,8 @@ def reference_cpu(wl, steps, warmup, n_obj):
     t_obj = max(t_step - t_shared, 0.0) / n_obj
     frame_s = t_shared + k * t_obj
     return {'value': 1.0 / frame_s, 'unit': 'frames/s', 'cores': cores, 'kind': 'reference',
-            'extrapolated': n_obj < k,
+            'extrapolated': n_obj < k, 'steps_requested': requested, 'steps_timed': steps, 'truncated': steps < requested,
+            'memory_frames_in_sample': mem_frames,  # a memory frame adds the value encoder; 0 of them = an optimistic CPU figure
             'sample': f'{steps} timed (+{warmup} warm-up) steps of the unmodified reference DEVAInferenceCore.step (oracle/_ref, '
                       f'fp32, torch {torch.__version__}, {cores} threads) on full {wl["h"]}x{wl["w"]} frames, N={wl["n"]} slots, '
                       f'{n_obj} of {k} objects per step, every 5th step a memory frame; full-frame time = shared + {k} x per-object, '
