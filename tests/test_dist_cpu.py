@@ -88,3 +88,50 @@ def test_sharded_core_partitions():
             assert owned == list(range(k))
             per = -(-k // world) if k else 0
             assert all(b - a <= per for a, b in cover)
+
+
+def _sharded_read_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from oracle import memory_math as mm
+    from oracle import sharded
+    torch.manual_seed(0)  # every rank draws the same bank and queries, then keeps its slice
+    ck, cv, k_obj, n, q, top_k = 16, 8, 5, 203, 37, 30
+    mem_key, mem_shr = torch.randn(ck, n, dtype=torch.float64), 1 + torch.rand(n, dtype=torch.float64)
+    values = torch.randn(k_obj * cv, n, dtype=torch.float64)
+    qk, qe = torch.randn(ck, q, dtype=torch.float64), torch.sigmoid(torch.randn(ck, q, dtype=torch.float64))
+    lo, hi = sharded.token_bounds(n, world, rank)
+    ro, usage, idx, w = sharded.sharded_read(mem_key[:, lo:hi], mem_shr[lo:hi], values[:, lo:hi], lo, qk, qe, top_k, k_obj)
+    ref_ro, ref_usage, ref_idx, ref_w = mm.read(mem_key, mem_shr, qk, qe, values, top_k)
+    per = -(-k_obj // world)
+    a, b = min(k_obj, rank * per), min(k_obj, (rank + 1) * per)
+    err_ro = float((ro - ref_ro[a * cv:b * cv]).abs().max()) if b > a else 0.0
+    err_use = float((usage - ref_usage[lo:hi]).abs().max())
+    same_set = bool((idx.sort(0)[0] == ref_idx.sort(0)[0]).all())
+    err_w = float((w - ref_w).abs().max())
+    # consolidation softmax over column slices of a [P, n] similarity
+    sim = torch.randn(6, n, dtype=torch.float64) * 3
+    pw = sharded.sharded_row_softmax(sim[:, lo:hi])
+    err_sm = float((pw - torch.softmax(sim, dim=1)[:, lo:hi]).abs().max())
+    out[rank] = (err_ro, err_use, same_set, err_w, err_sm, tuple(ro.shape))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bank_sharded_read_protocol_four_ranks():
+    """The collective protocol of the bank-sharded read (local top-k -> all-gather -> global top-k + softmax -> partial
+    read-out -> reduce-scatter by object) and of the sharded consolidation softmax, restated in oracle/sharded.py, equals the
+    unsharded reference math at world size 4 with ragged token / object partitions (203 slots, 5 objects)."""
+    import sys
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, here)
+    world = 4
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sharded_read_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    shapes = []
+    for r in range(world):
+        err_ro, err_use, same_set, err_w, err_sm, shape = out[r]
+        assert err_ro < 1e-12 and err_use < 1e-12 and same_set and err_w < 1e-12 and err_sm < 1e-12, (r, out[r])
+        shapes.append(shape[0])
+    assert shapes == [16, 16, 8, 0]  # 5 objects in blocks of 2: ranks own 2, 2, 1, 0 objects (CV = 8)
