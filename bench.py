@@ -627,7 +627,7 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def reference_cpu(wl, steps, warmup, n_obj, budget_s=240.0):
+def reference_cpu(wl, steps, warmup, n_obj, budget_s=150.0):
     """The reference's own step() on the host cores.  A step of the sample is one full-resolution frame of the named
     workload with ``n_obj`` of its K objects; every per-object stage of DEVA is independent across objects (the
     reference's own note, docs/DEMO.md:41: run time is linear in the number of objects), so the full-frame time is
