@@ -725,13 +725,16 @@ def _run_leg(args_list, timeout):
 
 def _run_dist_leg(args_list, timeout):
     """Every rank of a torchrun launch calls this: each starts ONE child of this script with its own RANK / LOCAL_RANK /
-    WORLD_SIZE and the next rendezvous port, so the children form their own process group (rank 0's child hosts the store:
+    WORLD_SIZE and a rendezvous port of its own, so the children form their own process group (rank 0's child hosts the store:
     the elastic agent's variables are dropped).  Returns the child's JSON line on rank 0 ({'error': ...} when the leg
     failed or timed out), None elsewhere.  Never raises."""
     rank = int(os.environ.get('RANK', 0))
     env = {k: v for k, v in os.environ.items() if not k.startswith('TORCHELASTIC')}
     env['MASTER_ADDR'] = os.environ.get('MASTER_ADDR', '127.0.0.1')
-    env['MASTER_PORT'] = str(int(os.environ.get('MASTER_PORT', '29500')) + 1)
+    port = int(os.environ.get('MASTER_PORT', '29500'))
+    # well away from the launcher's port: a driver that walks P, P+1, ... for its N = 1, 2, 4, 8 launches must not find
+    # the children's store port in TIME_WAIT
+    env['MASTER_PORT'] = str(port + 1537 if port + 1537 < 65000 else port - 1537)
     cmd = [sys.executable, os.path.abspath(__file__)] + args_list
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
