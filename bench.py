@@ -330,8 +330,12 @@ def run_ours(args):
     # the clock sampler starts BEFORE the warm-up: nvidia-smi's start-up (NVML initialisation takes driver locks) must not
     # fall into the timed region; only samples taken during the timed region are kept (ClockSampler.mark)
     sampler = ClockSampler(local) if rank == 0 else None
-    n_warm = max(args.warmup, 6)  # >= one full mem_every period: the timed region sees no first-time allocation / kernel load
-    for _ in range(n_warm):
+    # Setup steps + the requested warm-up together cover at least one full mem_every period (6 steps): the first regular
+    # memory frame grows the allocator's pools, which must not happen inside the timed region.  `warmup` in the JSON line is
+    # the requested W (at least 3); the untimed steps before it (clip initialisation + priming) are counted in `setup_steps`.
+    n_warm = max(args.warmup, 3)
+    n_prime = max(0, 6 - n_warm)
+    for _ in range(n_prime + n_warm):
         clip.step_resident()
     torch.cuda.synchronize()
     if sampler:
@@ -407,7 +411,7 @@ def run_ours(args):
             'steps': args.steps, 'warmup': n_warm, 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f16 MMA operands / f32 accumulate '
             f'(tcgen05 memory read + conv stack), precision plan {precision!r}; key path split-f16x3 (~f32)', 'data': 'synthetic',
-            'config': workload_config(wl, clip.q, world),
+            'config': workload_config(wl, clip.q, world), 'setup_steps': 1 + n_prime,
             'roofline': {'kernel': 'fused affinity path: pack_query + sim_topk(tcgen05 fp16x3) + merge + bucket + readout_sparse(tcgen05, '
                                    'affinity tiles built in smem); traffic = DRAM bytes of readout_sparse_kernel (ncu, the fp16 '
                                    'token-major output variant the step runs)',
@@ -640,11 +644,14 @@ def reference_cpu(wl, steps, warmup, n_obj, budget_s=150.0):
     t_build = time.perf_counter()
     clip = RefClip(wl, 'cpu', n_obj, seed=100)
     t_build = time.perf_counter() - t_build
-    t_warm = 0.0
-    for _ in range(warmup):
+    t_warm, warm_done, t_warm_all = 0.0, 0, time.perf_counter()
+    for _ in range(warmup):  # at least one; no further ones once a minute has gone into warming up
         t0 = time.perf_counter()
         clip.step()
         t_warm = time.perf_counter() - t0
+        warm_done += 1
+        if time.perf_counter() - t_warm_all > 60.0:
+            break
     # time budget of the timed region (a sample step is 4 s on a fast 64-core box, 30 s on a slow 128-core one): never fewer
     # than 2 steps, never more than requested; a shortened run is flagged and the value stays a per-step average
     requested = steps
@@ -664,8 +671,9 @@ def reference_cpu(wl, steps, warmup, n_obj, budget_s=150.0):
     frame_s = t_shared + k * t_obj
     return {'value': 1.0 / frame_s, 'unit': 'frames/s', 'cores': cores, 'kind': 'reference',
             'extrapolated': n_obj < k, 'steps_requested': requested, 'steps_timed': steps, 'truncated': steps < requested,
+            'warmup_requested': warmup, 'warmup_done': warm_done,
             'memory_frames_in_sample': mem_frames,  # a memory frame adds the value encoder; 0 of them = an optimistic CPU figure
-            'sample': f'{steps} timed (+{warmup} warm-up) steps of the unmodified reference DEVAInferenceCore.step (oracle/_ref, '
+            'sample': f'{steps} timed (+{warm_done} warm-up) steps of the unmodified reference DEVAInferenceCore.step (oracle/_ref, '
                       f'fp32, torch {torch.__version__}, {cores} threads) on full {wl["h"]}x{wl["w"]} frames, N={wl["n"]} slots, '
                       f'{n_obj} of {k} objects per step, every 5th step a memory frame; full-frame time = shared + {k} x per-object, '
                       f'both measured',
@@ -763,12 +771,16 @@ def run_reference(args):
         base = reference_cpu(wl, args.steps, max(args.warmup, 1), args.ref_objects)
         q = base.pop('q')
         ms_step = base['measured']['s_per_sample_step'] * 1e3
+        steps_done, warm_done = base['steps_timed'], base['warmup_done']
     else:  # staged copy missing: the oracle port, stage by stage (kind 'port')
         base = cpu_baseline_port(wl, budget_s=40.0)
         q = (-(-wl['h'] // 16)) * (-(-wl['w'] // 16))
         ms_step = 1e3 / base['value']
+        steps_done, warm_done = 1, 0
     out = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'frames/s', 'n_gpus': world,
-           'steps': args.steps, 'warmup': max(args.warmup, 1), 'ms_per_step': ms_step, 'higher_is_better': True,
+           # the steps / warm-up actually EXECUTED (= the requested ones unless the time budget shortened the run, see
+           # cpu_baseline.truncated): ms_per_step * steps is the timed wall
+           'steps': steps_done, 'warmup': warm_done, 'ms_per_step': ms_step, 'higher_is_better': True,
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
            'extrapolated': bool(base.get('extrapolated', True)),
            'ms_per_step_is': 'measured time of one SAMPLE step (see cpu_baseline.sample); value = 1 / (shared + K x per-object)',
