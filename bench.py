@@ -40,6 +40,10 @@ for _p in (ROOT, PKG):
 import torch  # noqa: E402
 
 CK, CV, TOP_K = 64, 512, 30
+try:  # the cores this process may use BEFORE a rank pins itself next to its GPU: the CPU baseline legs get all of them back
+    ALL_CORES = os.sched_getaffinity(0)
+except Exception:
+    ALL_CORES = None
 WORKLOADS = {
     'c3': dict(name='c3: 1080p, 16 objects, 10k memory slots, full encode->read->decode', h=1080, w=1920, k=16,
                n=10000),
@@ -724,7 +728,13 @@ def _run_leg(args_list, timeout):
     env = dict(os.environ)
     for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT'):
         env.pop(k, None)
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    def unpin():  # run_ours pinned this process to its GPU's NUMA node; a baseline leg may use every host core
+        if ALL_CORES:
+            try:
+                os.sched_setaffinity(0, ALL_CORES)
+            except Exception:
+                pass
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, preexec_fn=unpin)
     for line in reversed(r.stdout.strip().splitlines()):
         if line.startswith('{'):
             return json.loads(line)
