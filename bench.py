@@ -37,13 +37,16 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-import torch  # noqa: E402
-
-CK, CV, TOP_K = 64, 512, 30
-try:  # the cores this process may use BEFORE a rank pins itself next to its GPU: the CPU baseline legs get all of them back
+try:  # a baseline leg started by a pinned parent (see _run_leg) gets every host core back, before torch sizes its pools
+    if os.environ.get('DEVA_B200_BENCH_CORES'):
+        os.sched_setaffinity(0, {int(c) for c in os.environ['DEVA_B200_BENCH_CORES'].split(',')})
     ALL_CORES = os.sched_getaffinity(0)
 except Exception:
     ALL_CORES = None
+
+import torch  # noqa: E402
+
+CK, CV, TOP_K = 64, 512, 30
 WORKLOADS = {
     'c3': dict(name='c3: 1080p, 16 objects, 10k memory slots, full encode->read->decode', h=1080, w=1920, k=16,
                n=10000),
@@ -728,13 +731,9 @@ def _run_leg(args_list, timeout):
     env = dict(os.environ)
     for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT'):
         env.pop(k, None)
-    def unpin():  # run_ours pinned this process to its GPU's NUMA node; a baseline leg may use every host core
-        if ALL_CORES:
-            try:
-                os.sched_setaffinity(0, ALL_CORES)
-            except Exception:
-                pass
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, preexec_fn=unpin)
+    if ALL_CORES:  # run_ours pinned this process to its GPU's NUMA node; a baseline leg may use every host core (the child
+        env['DEVA_B200_BENCH_CORES'] = ','.join(str(c) for c in sorted(ALL_CORES))  # re-opens its mask before importing torch)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     for line in reversed(r.stdout.strip().splitlines()):
         if line.startswith('{'):
             return json.loads(line)
